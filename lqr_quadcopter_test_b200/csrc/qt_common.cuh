@@ -1,0 +1,60 @@
+// qt_common.cuh — context object and launch helpers shared by the translation units of libqtrack.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/qtrack.h"
+
+struct qt_context {
+    int device;
+    cudaStream_t stream;      // stream work is enqueued on
+    cudaStream_t own_stream;  // created by qt_create, destroyed by qt_destroy
+    int sm_count;
+    int64_t launches;
+    // scratch owned by the library (host-buffer entry points only; never handed to the caller)
+    void *scratch_dev;
+    size_t scratch_bytes;
+    void *partials_dev;       // qt_reduce_summary block partials (partials_cap x 16 doubles)
+    int partials_cap;
+    char err[512];
+};
+
+namespace qt {
+
+inline int fail(qt_context *ctx, int code, const char *what, const char *detail) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+
+inline int check_launch(qt_context *ctx, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, QT_ERR_CUDA, what, cudaGetErrorString(e));
+    ctx->launches += 1;
+    return QT_OK;
+}
+
+#define QT_CUDA_TRY(ctx, expr)                                                    \
+    do {                                                                          \
+        cudaError_t qt_e_ = (expr);                                               \
+        if (qt_e_ != cudaSuccess) return qt::fail((ctx), QT_ERR_CUDA, #expr, cudaGetErrorString(qt_e_)); \
+    } while (0)
+
+#define QT_REQUIRE(ctx, cond, msg)                                     \
+    do {                                                               \
+        if (!(cond)) return qt::fail((ctx), QT_ERR_ARG, "invalid argument", msg); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace qt

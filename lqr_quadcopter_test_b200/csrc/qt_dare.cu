@@ -1,0 +1,496 @@
+// qt_dare.cu — batched fp64 DARE solver for many small systems.
+//
+// Replaces solve_dare (controllers/riccati_lqr.py:119-184), i.e. scipy.linalg.solve_discrete_are
+// followed by K = (R + B'PB)^-1 B'PA, for the thousands of n = 6 / n = 9 systems a Q/R sweep
+// generates (controllers/tuning.py:846-857 builds one controller, hence one DARE, per candidate).
+//
+// Algorithm: structure-preserving doubling (SDA) on (A_k, G_k, H_k), G_0 = B R^-1 B', H_0 = Q:
+//     W = I + G_k H_k;  X = W^-1 A_k;  Y = W^-1 G_k
+//     A_{k+1} = A_k X;  G_{k+1} = G_k + A_k Y A_k';  H_{k+1} = H_k + A_k' H_k X
+// H_k converges quadratically to P (14-18 doublings on the tuning ranges).  scipy uses an
+// ordered QZ decomposition of the 2n x 2n symplectic pencil instead; both compute the same
+// stabilising solution, agreement is checked to 1e-9 relative on K (tests/test_dare_gpu.py).
+//
+// Mapping: these are tiny, non-GEMM solves — no tensor cores.  A "team" of N lanes of one
+// warp owns one system, lane i holding row i of every matrix in registers; 32/N systems share a
+// warp.  Products need the other lanes' rows, which are staged in shared memory (padded row
+// stride, 16-byte LDS broadcasts); W is inverted by Gauss-Jordan elimination with partial
+// pivoting carried out across the team (pivot search and pivot-row broadcast through shared
+// memory, __syncwarp between phases).  n and m are zero-padded to the next instantiated N,
+// which leaves the solution of the original system unchanged (block-diagonal embedding).
+#include "qt_common.cuh"
+
+namespace qt {
+
+constexpr int kDareWarps = 4;
+constexpr int kDareMaxIter = 64;
+constexpr double kDareTol = 1e-14;  // relative Frobenius change of H
+
+struct DareArgs {
+    int n, m;
+    int64_t batch;
+    const double *A, *B, *Q, *R;
+    int64_t sA, sB, sQ, sR;
+    double *P, *K;
+    int32_t *iters, *info;
+};
+
+template <int N>
+struct Lay {
+    static constexpr int LD = (N + 1) & ~1;        // even row stride: rows stay 16-byte aligned
+    static constexpr int MAT = N * LD;
+    static constexpr int TEAM = 6 * MAT + 4 * LD;  // sA sG sH sX sY sS | pivot row (3 LD) | column (LD)
+    static constexpr int TEAMS = 32 / N;           // systems per warp
+    static constexpr int SLOTS = TEAMS + ((32 % N) ? 1 : 0);  // + a ghost team for leftover lanes
+};
+
+// c[j] (+)= sum_k x[k] * Y[k][j],  Y row-major in shared memory
+template <int N, bool ACCUM>
+__device__ __forceinline__ void row_times(const double (&x)[N], const double *__restrict__ Y,
+                                          double (&c)[N]) {
+    constexpr int LD = Lay<N>::LD;
+    if (!ACCUM) {
+#pragma unroll
+        for (int j = 0; j < N; j++) c[j] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            const double2 y = *reinterpret_cast<const double2 *>(Y + k * LD + j);
+            c[j] = fma(x[k], y.x, c[j]);
+            if (j + 1 < N) c[j + 1] = fma(x[k], y.y, c[j + 1]);
+        }
+    }
+}
+
+// c[j] += sum_k x[k] * Y[j][k]   (product with the transpose of Y)
+template <int N>
+__device__ __forceinline__ void row_times_T(const double (&x)[N], const double *__restrict__ Y,
+                                            double (&c)[N]) {
+    constexpr int LD = Lay<N>::LD;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double acc = c[j];
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            const double2 y = *reinterpret_cast<const double2 *>(Y + j * LD + k);
+            acc = fma(x[k], y.x, acc);
+            if (k + 1 < N) acc = fma(x[k + 1], y.y, acc);
+        }
+        c[j] = acc;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_row(double *__restrict__ M, int row, const double (&x)[N]) {
+    constexpr int LD = Lay<N>::LD;
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        double2 v;
+        v.x = x[j];
+        v.y = (j + 1 < N) ? x[j + 1] : 0.0;
+        *reinterpret_cast<double2 *>(M + row * LD + j) = v;
+    }
+}
+
+// Gauss-Jordan with partial pivoting, one matrix row per lane.  On exit the lane that served
+// as pivot for column c holds row c of W^-1 [R1 | R2] in (r1 | r2); it writes them to
+// X[c][:] / Y[c][:].  Returns false if a pivot was zero / not finite.
+template <int N, bool TWO>
+__device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], double (&r2)[N],
+                                             double *__restrict__ sRow, double *__restrict__ sCol,
+                                             double *__restrict__ X, double *__restrict__ Y, int li) {
+    constexpr int LD = Lay<N>::LD;
+    bool used = false, ok = true;
+    int my_col = 0;
+    double my_piv = 1.0;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        sCol[li] = used ? -1.0 : fabs(w[c]);
+        __syncwarp();
+        int p = 0;
+        double best = sCol[0];
+#pragma unroll
+        for (int k = 1; k < N; k++) {
+            const double v = sCol[k];
+            if (v > best) {
+                best = v;
+                p = k;
+            }
+        }
+        if (!(best > 0.0) || !(best < 1.0e300)) ok = false;
+        if (li == p) {
+            used = true;
+            my_col = c;
+            my_piv = w[c];
+            // only columns > c of W are still needed by the other rows
+#pragma unroll
+            for (int j = c & ~1; j < N; j += 2) {
+                double2 v;
+                v.x = w[j];
+                v.y = (j + 1 < N) ? w[j + 1] : 0.0;
+                *reinterpret_cast<double2 *>(sRow + j) = v;
+            }
+            store_row<N>(sRow + LD, 0, r1);
+            if (TWO) store_row<N>(sRow + 2 * LD, 0, r2);
+        }
+        __syncwarp();
+        if (li != p) {
+            const double f = w[c] / sRow[c];
+#pragma unroll
+            for (int j = c + 1; j < N; j++) w[j] = fma(-f, sRow[j], w[j]);
+            w[c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                const double2 y = *reinterpret_cast<const double2 *>(sRow + LD + j);
+                r1[j] = fma(-f, y.x, r1[j]);
+                if (j + 1 < N) r1[j + 1] = fma(-f, y.y, r1[j + 1]);
+            }
+            if (TWO) {
+#pragma unroll
+                for (int j = 0; j < N; j += 2) {
+                    const double2 y = *reinterpret_cast<const double2 *>(sRow + 2 * LD + j);
+                    r2[j] = fma(-f, y.x, r2[j]);
+                    if (j + 1 < N) r2[j + 1] = fma(-f, y.y, r2[j + 1]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    const double inv = 1.0 / my_piv;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        r1[j] *= inv;
+        if (TWO) r2[j] *= inv;
+    }
+    store_row<N>(X, my_col, r1);
+    if (TWO) store_row<N>(Y, my_col, r2);
+    __syncwarp();
+    return ok;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_constant__ DareArgs D) {
+    extern __shared__ __align__(16) double smem[];
+    using L = Lay<N>;
+    constexpr int LD = L::LD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int team = lane / N, li = lane % N;
+    const int64_t sys = ((int64_t)blockIdx.x * kDareWarps + warp) * L::TEAMS + team;
+    const int n = D.n, m = D.m;
+    bool ghost = (team >= L::TEAMS) || (sys >= D.batch);
+    if (!ghost && D.info[sys] == 3) ghost = true;  // rejected by the validation kernel
+
+    double *tb = smem + (size_t)(warp * L::SLOTS + team) * L::TEAM;
+    double *sA = tb, *sG = tb + L::MAT, *sH = tb + 2 * L::MAT, *sX = tb + 3 * L::MAT,
+           *sY = tb + 4 * L::MAT, *sS = tb + 5 * L::MAT, *sRow = tb + 6 * L::MAT,
+           *sCol = tb + 6 * L::MAT + 3 * LD;
+
+    const double *Ap = ghost ? nullptr : D.A + sys * D.sA;
+    const double *Bp = ghost ? nullptr : D.B + sys * D.sB;
+    const double *Qp = ghost ? nullptr : D.Q + sys * D.sQ;
+    const double *Rp = ghost ? nullptr : D.R + sys * D.sR;
+
+    double a[N], g[N], h[N], brow[N];
+    bool ok = true;
+    {
+        // R_pad = blockdiag(R, I), rows of B'_pad as right-hand side:  Z = R^-1 B'
+        double w[N], r1[N], r2[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const bool in_a = !ghost && li < n && j < n;
+            a[j] = in_a ? Ap[li * n + j] : 0.0;
+            h[j] = in_a ? Qp[li * n + j] : 0.0;
+            brow[j] = (!ghost && li < n && j < m) ? Bp[li * m + j] : 0.0;
+            w[j] = (!ghost && li < m && j < m) ? Rp[li * m + j] : (li == j ? 1.0 : 0.0);
+            r1[j] = (!ghost && li < m && j < n) ? Bp[j * m + li] : 0.0;
+            r2[j] = 0.0;
+        }
+        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sCol, sX, sY, li);
+        row_times<N, false>(brow, sX, g);  // G0 = B Z
+    }
+
+    bool conv = false;
+    int iters = 0;
+    for (int it = 0; it < kDareMaxIter; it++) {
+        if (__all_sync(0xffffffffu, conv || ghost)) break;
+        store_row<N>(sA, li, a);
+        store_row<N>(sG, li, g);
+        store_row<N>(sH, li, h);
+        __syncwarp();
+        double an[N], gn[N], hn[N];
+        {
+            double w[N], r1[N], r2[N];
+            row_times<N, false>(g, sH, w);  // G H
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                w[j] += (j == li) ? 1.0 : 0.0;  // W = I + G H
+                r1[j] = a[j];
+                r2[j] = g[j];
+            }
+            ok &= gauss_jordan<N, true>(w, r1, r2, sRow, sCol, sX, sY, li);  // X = W^-1 A, Y = W^-1 G
+        }
+        row_times<N, false>(a, sX, an);  // A X
+        {
+            double t[N];
+            row_times<N, false>(a, sY, t);  // A Y
+#pragma unroll
+            for (int j = 0; j < N; j++) gn[j] = g[j];
+            row_times_T<N>(t, sA, gn);  // G + (A Y) A'
+        }
+        {
+            double s[N];
+            row_times<N, false>(h, sX, s);  // H X
+            store_row<N>(sS, li, s);
+            __syncwarp();
+            // H + A' (H X): row i needs column i of A
+            double acol[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) acol[k] = sA[k * LD + li];
+#pragma unroll
+            for (int j = 0; j < N; j++) hn[j] = h[j];
+            row_times<N, true>(acol, sS, hn);
+        }
+        // convergence: ||H+ - H||_F <= tol ||H+||_F, reduced over the team through sCol
+        double d2 = 0.0, h2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const double d = hn[j] - h[j];
+            d2 = fma(d, d, d2);
+            h2 = fma(hn[j], hn[j], h2);
+        }
+        sRow[li] = d2;
+        sRow[LD + li] = h2;
+        __syncwarp();
+        double D2 = 0.0, H2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            D2 += sRow[k];
+            H2 += sRow[LD + k];
+        }
+        __syncwarp();
+        if (!conv) {
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                a[j] = an[j];
+                g[j] = gn[j];
+                h[j] = hn[j];
+            }
+            iters = it + 1;
+            if (D2 <= kDareTol * kDareTol * H2) conv = true;
+            if (!(D2 == D2)) conv = true;  // NaN: stop, reported through info
+            if (!(D2 == D2)) ok = false;
+        }
+    }
+
+    // P = (H + H') / 2
+    store_row<N>(sH, li, h);
+    __syncwarp();
+    double p[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) p[j] = 0.5 * (h[j] + sH[j * LD + li]);
+    if (!ghost && D.P && li < n) {
+#pragma unroll
+        for (int j = 0; j < N; j++)
+            if (j < n) D.P[sys * (int64_t)n * n + li * n + j] = p[j];
+    }
+
+    // K = (R + B'PB)^-1 B'PA
+    {
+        double a0[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) a0[j] = (!ghost && li < n && j < n) ? Ap[li * n + j] : 0.0;
+        __syncwarp();
+        store_row<N>(sA, li, a0);
+        store_row<N>(sS, li, brow);
+        __syncwarp();
+        double pb[N], pa[N];
+        row_times<N, false>(p, sS, pb);  // P B
+        row_times<N, false>(p, sA, pa);  // P A
+        store_row<N>(sX, li, pb);
+        store_row<N>(sY, li, pa);
+        __syncwarp();
+        double bcol[N], w[N], r1[N], r2[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) bcol[k] = sS[k * LD + li];  // column i of B = row i of B'
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            w[j] = (!ghost && li < m && j < m) ? Rp[li * m + j] : (li == j ? 1.0 : 0.0);
+            r2[j] = 0.0;
+        }
+        row_times<N, true>(bcol, sX, w);    // R + B'(PB)
+        row_times<N, false>(bcol, sY, r1);  // B'(PA)
+        __syncwarp();
+        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sCol, sG, sH, li);  // K rows -> sG
+        if (!ghost && D.K && li < m) {
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                if (j < n) D.K[sys * (int64_t)m * n + li * n + j] = sG[li * LD + j];
+        }
+    }
+    if (!ghost && li == 0) {
+        D.iters[sys] = iters;
+        D.info[sys] = !ok ? 2 : (conv ? 0 : 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Validation (riccati_lqr.py:57-116): Q symmetric (np.allclose atol 1e-8, rtol 1e-5) with
+// eigenvalues >= -1e-10, R symmetric with eigenvalues > 1e-10.  One thread per system.  Exactly
+// diagonal matrices (what q_pos/q_vel/q_int/r_controls produce, riccati_lqr.py:620-700) are
+// decided from the diagonal; anything else runs cyclic Jacobi sweeps.
+__device__ double min_eig_sym(const double *M, int n, int ld) {
+    double a[QT_MAX_N * QT_MAX_N];
+    bool diag = true;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            // eigvalsh reads the lower triangle only
+            const double v = (j <= i) ? M[i * ld + j] : M[j * ld + i];
+            a[i * n + j] = v;
+            if (i != j && v != 0.0) diag = false;
+        }
+    if (!diag) {
+        for (int sweep = 0; sweep < 30; sweep++) {
+            double off = 0.0, dg = 0.0;
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) {
+                    if (i != j) off += a[i * n + j] * a[i * n + j];
+                    else dg += a[i * n + j] * a[i * n + j];
+                }
+            if (off <= 1e-32 * dg || off == 0.0) break;
+            for (int p = 0; p < n - 1; p++)
+                for (int q = p + 1; q < n; q++) {
+                    const double apq = a[p * n + q];
+                    if (apq == 0.0) continue;
+                    const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                    for (int k = 0; k < n; k++) {
+                        const double akp = a[k * n + p], akq = a[k * n + q];
+                        a[k * n + p] = c * akp - s * akq;
+                        a[k * n + q] = s * akp + c * akq;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        const double apk = a[p * n + k], aqk = a[q * n + k];
+                        a[p * n + k] = c * apk - s * aqk;
+                        a[q * n + k] = s * apk + c * aqk;
+                    }
+                }
+        }
+    }
+    double mn = a[0];
+    for (int i = 1; i < n; i++) mn = fmin(mn, a[i * n + i]);
+    for (int i = 0; i < n; i++)
+        if (!(a[i * n + i] == a[i * n + i])) mn = a[i * n + i];
+    return mn;
+}
+
+__device__ bool allclose_sym(const double *M, int n) {
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            const double x = M[i * n + j], y = M[j * n + i];
+            if (!(fabs(x - y) <= 1e-8 + 1e-5 * fabs(y))) return false;  // also rejects NaN
+        }
+    return true;
+}
+
+__global__ void dare_validate_kernel(const __grid_constant__ DareArgs D) {
+    const int64_t sys = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= D.batch) return;
+    // shared Q / R (stride 0) need to be checked only once, but the check is cheap: keep it simple
+    const double *Q = D.Q + sys * D.sQ, *R = D.R + sys * D.sR;
+    bool ok = allclose_sym(Q, D.n) && allclose_sym(R, D.m);
+    if (ok) {
+        const double qmin = min_eig_sym(Q, D.n, D.n);
+        const double rmin = min_eig_sym(R, D.m, D.m);
+        ok = !(qmin < -1e-10) && (qmin == qmin) && (rmin > 1e-10);
+    }
+    D.info[sys] = ok ? 0 : 3;
+    D.iters[sys] = 0;
+}
+
+template <int N>
+static cudaError_t launch_dare(const DareArgs &D, cudaStream_t st) {
+    using L = Lay<N>;
+    const size_t smem = (size_t)kDareWarps * L::SLOTS * L::TEAM * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(dare_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t per_block = (int64_t)kDareWarps * L::TEAMS;
+    const int64_t blocks = (D.batch + per_block - 1) / per_block;
+    dare_kernel<N><<<(unsigned)blocks, kDareWarps * 32, smem, st>>>(D);
+    return cudaGetLastError();
+}
+
+// riccati_lqr.py:187-316 and 602-700 for a batch of diagonal weights
+__global__ void build_lqr_systems_kernel(int n, int64_t batch, double dt, double mass, double gravity,
+                                         const double *__restrict__ q_diag, const double *__restrict__ r_diag,
+                                         double *__restrict__ A, double *__restrict__ B,
+                                         double *__restrict__ Q, double *__restrict__ R) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        for (int r = 0; r < n; r++)
+            for (int c = 0; c < n; c++) A[r * n + c] = (r == c) ? 1.0 : 0.0;
+        for (int k = 0; k < 3; k++) A[k * n + 3 + k] = 1.0 * dt;  // A_d = I + A_c dt
+        for (int r = 0; r < n; r++)
+            for (int c = 0; c < 4; c++) B[r * 4 + c] = 0.0;
+        B[5 * 4 + 0] = (1.0 / mass) * dt;
+        B[4 * 4 + 1] = -gravity * dt;
+        B[3 * 4 + 2] = gravity * dt;
+        if (n == 9)
+            for (int k = 0; k < 3; k++) A[(6 + k) * n + k] = 1.0 * dt;  // integral rows: C dt
+    }
+    if (i >= batch) return;
+    double *Qi = Q + i * n * n, *Ri = R + i * 16;
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) Qi[r * n + c] = (r == c) ? q_diag[i * n + r] : 0.0;
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) Ri[r * 4 + c] = (r == c) ? r_diag[i * 4 + r] : 0.0;
+}
+
+}  // namespace qt
+
+using namespace qt;
+
+extern "C" int qt_dare_batched(qt_context *ctx, int32_t n, int32_t m, int64_t batch,
+                               const double *A_dev, int64_t strideA, const double *B_dev,
+                               int64_t strideB, const double *Q_dev, int64_t strideQ,
+                               const double *R_dev, int64_t strideR, double *P_out_dev,
+                               double *K_out_dev, int32_t *iters_out_dev, int32_t *info_out_dev) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, n >= 1 && n <= QT_MAX_N && m >= 1 && m <= QT_MAX_M, "n must be 1..16, m 1..8");
+    QT_REQUIRE(ctx, batch >= 0, "batch < 0");
+    QT_REQUIRE(ctx, A_dev && B_dev && Q_dev && R_dev && iters_out_dev && info_out_dev, "null pointer");
+    if (batch == 0) return QT_OK;
+    DareArgs D{n, m, batch, A_dev, B_dev, Q_dev, R_dev, strideA, strideB, strideQ, strideR,
+               P_out_dev, K_out_dev, iters_out_dev, info_out_dev};
+    DeviceGuard guard(ctx->device);
+    dare_validate_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(D);
+    int rc = check_launch(ctx, "dare_validate_kernel");
+    if (rc) return rc;
+    const int need = n > m ? n : m;
+    cudaError_t err;
+    if (need <= 4) err = launch_dare<4>(D, ctx->stream);
+    else if (need <= 6) err = launch_dare<6>(D, ctx->stream);
+    else if (need <= 9) err = launch_dare<9>(D, ctx->stream);
+    else if (need <= 12) err = launch_dare<12>(D, ctx->stream);
+    else err = launch_dare<16>(D, ctx->stream);
+    if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "dare_kernel launch", cudaGetErrorString(err));
+    ctx->launches += 1;
+    return QT_OK;
+}
+
+extern "C" int qt_build_lqr_systems(qt_context *ctx, int32_t n, int64_t batch, double dt, double mass,
+                                    double gravity, const double *q_diag_dev, const double *r_diag_dev,
+                                    double *A_out_dev, double *B_out_dev, double *Q_out_dev,
+                                    double *R_out_dev) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, n == 6 || n == 9, "n must be 6 (LQR) or 9 (LQI)");
+    QT_REQUIRE(ctx, batch >= 0 && q_diag_dev && r_diag_dev && A_out_dev && B_out_dev && Q_out_dev && R_out_dev,
+               "bad argument");
+    DeviceGuard guard(ctx->device);
+    const int64_t threads = batch > 0 ? batch : 1;
+    build_lqr_systems_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+        n, batch, dt, mass, gravity, q_diag_dev, r_diag_dev, A_out_dev, B_out_dev, Q_out_dev, R_out_dev);
+    return check_launch(ctx, "build_lqr_systems_kernel");
+}

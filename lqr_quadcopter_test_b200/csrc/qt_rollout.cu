@@ -1,0 +1,316 @@
+// qt_rollout.cu — the fused closed-loop rollout kernel.
+//
+// Replaces the reference's hot loop
+//     while not done: action = controller.compute_action(obs); obs, r, done, info = env.step(action)
+// (eval.py:119-165, controllers/tuning.py:885-906) together with compute_episode_metrics
+// (utils/metrics.py:264-338) by ONE kernel launch for all episodes.
+//
+// Mapping: one thread per chain of episodes (normally one episode).  The 12-element state, the
+// LQI integrator, the target-pattern parameters, simulation time and every metric accumulator
+// stay in registers for all max_steps iterations; the gain matrix K of the block's episodes is
+// staged once in shared memory (reads are warp-uniform when k_stride is a multiple of 32).  HBM
+// is touched at the beginning (initial conditions), at the end (16 doubles per episode) and, in
+// the FULL variant only, for the optional strided trajectory log / teacher data set, which are
+// written struct-of-arrays so a warp's stores are contiguous.  The kernel is bound by the FP64
+// pipe; there is no GEMM-shaped work and no use for tensor cores.
+#include "qt_common.cuh"
+#include "qt_step.cuh"
+
+namespace qt {
+
+constexpr int kRolloutThreads = 128;
+
+struct RolloutArgs {
+    int64_t E, n_chains, chain, k_stride;
+    int max_steps;
+    int k_in_smem;
+    const double *state0, *tparams, *K;
+    double *metrics, *final_state, *traj;
+    float *feat, *actf;
+    int traj_stride, traj_slots, data_stride, data_slots;
+};
+
+template <int MOTION, bool LQI, bool FULL>
+__global__ void __launch_bounds__(kRolloutThreads)
+    rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ RolloutArgs A) {
+    extern __shared__ double sK[];
+    constexpr int KC = LQI ? 9 : 6;
+    const int64_t E = A.E;
+    const int64_t chain_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    int64_t g0 = 0;
+    if (A.k_in_smem) {
+        // chain == 1 here: the block covers episodes [b*T, b*T+T)
+        const int64_t ep0 = (int64_t)blockIdx.x * blockDim.x;
+        int64_t ep1 = ep0 + blockDim.x - 1;
+        if (ep1 > E - 1) ep1 = E - 1;
+        g0 = ep0 / A.k_stride;
+        const int64_t g1 = ep1 / A.k_stride;
+        const int n = (int)(g1 - g0 + 1) * 4 * KC;
+        const double *src = A.K + g0 * 4 * KC;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sK[i] = src[i];
+        __syncthreads();
+    }
+    if (chain_id >= A.n_chains) return;
+
+    DynConsts C;
+    C.init(P);
+    const double dt = P.dt;
+    const bool euler = FULL && (P.integrator == QT_INTEGRATOR_EULER);
+
+    double integ[3] = {0.0, 0.0, 0.0};
+    int saturations = 0;
+
+    const int64_t first = chain_id * A.chain;
+    int64_t last = first + A.chain;
+    if (last > E) last = E;
+
+    for (int64_t e = first; e < last; e++) {
+        double s[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = A.state0[(int64_t)i * E + e];
+        TargetGen<MOTION> tg;
+        tg.load(A.tparams, E, e);
+        const int64_t grp = e / A.k_stride;
+        const double *Kp = A.k_in_smem ? (sK + (grp - g0) * 4 * KC) : (A.K + grp * 4 * KC);
+        if (A.chain == 1) {  // controller.reset() before every episode (tuning.py:879)
+            integ[0] = integ[1] = integ[2] = 0.0;
+            saturations = 0;
+        }
+
+        double t = 0.0;
+        int step = 0, env_on = 0, met_on = 0, violations = 0, term = QT_TERM_NONE;
+        double sum_err = 0.0, sum_err2 = 0.0, max_err = 0.0, sum_eff = 0.0, err_post = 0.0;
+        // overshoot detector state (utils/metrics.py:205-261), streamed
+        bool prev_on = false, in_phase = false;
+        int streak = 0, ov_count = 0;
+        double ov_cur = 0.0, ov_max = 0.0;
+        int next_traj = 0, traj_slot = 0, next_data = 0, data_slot = 0;
+
+        double tp[3], tv[3], ta[3];
+        tg.template state<FULL>(P, t, tp, tv, ta);
+        double err_pre = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
+
+        while (term == QT_TERM_NONE && step < A.max_steps) {
+            // ---- controller on the pre-step observation
+            double act[4];
+            ctrl_action<LQI, FULL>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
+
+            // ---- metrics sample k = step (pre-step observation, eval.py:142-159)
+            {
+                const bool on = err_pre <= P.crit_target_radius;
+                met_on += on ? 1 : 0;
+                sum_err += err_pre;
+                sum_err2 += err_pre * err_pre;
+                max_err = (step == 0 || err_pre > max_err) ? err_pre : max_err;
+                sum_eff += sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
+                if (step > 0) {
+                    const double over = err_pre - P.crit_target_radius;
+                    if (prev_on && !on) {
+                        in_phase = true;
+                        streak = 1;
+                        ov_cur = over;
+                    } else if (in_phase && !on) {
+                        streak += 1;
+                        ov_cur = fmax(ov_cur, over);
+                    } else if (in_phase && on) {
+                        if (streak >= P.overshoot_window) {
+                            ov_count += 1;
+                            ov_max = fmax(ov_max, ov_cur);
+                        }
+                        in_phase = false;
+                        streak = 0;
+                        ov_cur = 0.0;
+                    }
+                }
+                prev_on = on;
+            }
+
+            bool log_traj = false;
+            if constexpr (FULL) {
+                if (A.traj && step == next_traj && traj_slot < A.traj_slots) {
+                    log_traj = true;
+                    double *row = A.traj + (int64_t)traj_slot * QT_TRAJ_FIELDS * E + e;
+#pragma unroll
+                    for (int i = 0; i < 12; i++) row[(int64_t)(QT_TRAJ_STATE + i) * E] = s[i];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        row[(int64_t)(QT_TRAJ_TARGET_P + i) * E] = tp[i];
+                        row[(int64_t)(QT_TRAJ_TARGET_V + i) * E] = tv[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) row[(int64_t)(QT_TRAJ_ACTION + i) * E] = act[i];
+                }
+                if (A.feat && step == next_data && data_slot < A.data_slots) {
+                    // deep_tracking_policy.py:241-286 feature layout, fp32
+                    float2 *f = reinterpret_cast<float2 *>(A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM);
+                    float2 *y = reinterpret_cast<float2 *>(A.actf + ((int64_t)data_slot * E + e) * QT_ACTION_DIM);
+                    float ft[18];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        ft[i] = (float)(tp[i] - s[i]);
+                        ft[3 + i] = (float)(tv[i] - s[3 + i]);
+                        ft[6 + i] = (float)s[6 + i];
+                        ft[9 + i] = (float)s[9 + i];
+                        ft[12 + i] = (float)tp[i];
+                        ft[15 + i] = (float)tv[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 9; i++) f[i] = make_float2(ft[2 * i], ft[2 * i + 1]);
+                    y[0] = make_float2((float)act[0], (float)act[1]);
+                    y[1] = make_float2((float)act[2], (float)act[3]);
+                    next_data += A.data_stride;
+                    data_slot += 1;
+                }
+            }
+
+            // ---- env.step (quadcopter_env.py:171-207)
+            double actv[4];
+            violations += validate_action(P, act, actv);
+            if (euler)
+                integrate_euler(C, dt, s, actv);
+            else
+                integrate_rk4(C, dt, s, actv);
+            constrain_state(P, C, s);
+            t += dt;
+            tg.template state<FULL>(P, t, tp, tv, ta);
+            err_post = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
+            term = termination_code(P, s, t);
+            env_on += (err_post <= P.env_target_radius) ? 1 : 0;
+            if constexpr (FULL) {
+                if (log_traj) {
+                    double *row = A.traj + (int64_t)traj_slot * QT_TRAJ_FIELDS * E + e;
+                    row[(int64_t)QT_TRAJ_TIME * E] = t;
+                    row[(int64_t)QT_TRAJ_ERR * E] = err_post;
+                    next_traj += A.traj_stride;
+                    traj_slot += 1;
+                }
+            }
+            step += 1;
+            err_pre = err_post;
+        }
+        if (in_phase && streak >= P.overshoot_window) {
+            ov_count += 1;
+            ov_max = fmax(ov_max, ov_cur);
+        }
+
+        const double n = (double)step;
+        const double env_ratio = step > 0 ? (double)env_on / n : 0.0;
+        const double met_ratio = step > 0 ? (double)met_on / n : 0.0;
+        double *m = A.metrics + e;
+        m[(int64_t)QT_M_STEPS * E] = n;
+        m[(int64_t)QT_M_FINAL_TIME * E] = t;
+        m[(int64_t)QT_M_ENV_ON_TARGET * E] = (double)env_on;
+        m[(int64_t)QT_M_MET_ON_TARGET * E] = (double)met_on;
+        m[(int64_t)QT_M_SUM_ERR * E] = sum_err;
+        m[(int64_t)QT_M_MAX_ERR * E] = max_err;
+        m[(int64_t)QT_M_SUM_ERR2 * E] = sum_err2;
+        m[(int64_t)QT_M_SUM_EFFORT * E] = sum_eff;
+        m[(int64_t)QT_M_OVERSHOOT_COUNT * E] = (double)ov_count;
+        m[(int64_t)QT_M_MAX_OVERSHOOT * E] = ov_max;
+        m[(int64_t)QT_M_ENV_SUCCESS * E] =
+            (t >= P.env_min_episode_duration && env_ratio >= P.env_min_on_target_ratio) ? 1.0 : 0.0;
+        m[(int64_t)QT_M_MET_SUCCESS * E] =
+            (step > 0 && t >= P.crit_min_episode_duration && met_ratio >= P.crit_min_on_target_ratio)
+                ? 1.0
+                : 0.0;
+        m[(int64_t)QT_M_TERMINATION * E] = (double)term;
+        m[(int64_t)QT_M_VIOLATIONS * E] = (double)violations;
+        m[(int64_t)QT_M_SATURATIONS * E] = (double)saturations;
+        m[(int64_t)QT_M_FINAL_ERR * E] = err_post;
+        if (A.final_state) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) A.final_state[(int64_t)i * E + e] = s[i];
+        }
+    }
+}
+
+template <int MOTION, bool LQI, bool FULL>
+static cudaError_t launch_one(const qt_params &P, const RolloutArgs &A, size_t smem, cudaStream_t st) {
+    const int64_t blocks = (A.n_chains + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks <= 0) return cudaSuccess;
+    rollout_kernel<MOTION, LQI, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, A);
+    return cudaGetLastError();
+}
+
+template <int MOTION>
+static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_t smem, bool full,
+                                 cudaStream_t st) {
+    if (P.use_lqi)
+        return full ? launch_one<MOTION, true, true>(P, A, smem, st)
+                    : launch_one<MOTION, true, false>(P, A, smem, st);
+    return full ? launch_one<MOTION, false, true>(P, A, smem, st)
+                : launch_one<MOTION, false, false>(P, A, smem, st);
+}
+
+}  // namespace qt
+
+extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
+                          int64_t chain, const double *state0_dev, const double *tparams_dev,
+                          const double *K_dev, int32_t k_cols, int64_t k_stride,
+                          double *metrics_out_dev, double *final_state_out_dev,
+                          double *traj_out_dev, int64_t traj_stride, int64_t traj_slots,
+                          float *feat_out_dev, float *act_out_dev, int64_t data_stride,
+                          int64_t data_slots) {
+    using namespace qt;
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
+    QT_REQUIRE(ctx, E >= 0 && max_steps >= 0 && max_steps < (1ll << 31), "bad E / max_steps");
+    QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
+    QT_REQUIRE(ctx, (feat_out_dev == nullptr) == (act_out_dev == nullptr), "feat/act must come together");
+    if (E == 0) return QT_OK;
+    if (chain < 1) chain = 1;
+    if (chain > E) chain = E;
+    if (k_stride < 1) k_stride = 1;
+    if (traj_stride < 1) traj_stride = 1;
+    if (data_stride < 1) data_stride = 1;
+    QT_REQUIRE(ctx, traj_stride < (1ll << 31) && data_stride < (1ll << 31) &&
+                        traj_slots < (1ll << 31) && data_slots < (1ll << 31), "log strides/slots");
+
+    RolloutArgs A;
+    A.E = E;
+    A.chain = chain;
+    A.n_chains = (E + chain - 1) / chain;
+    A.k_stride = k_stride;
+    A.max_steps = (int)max_steps;
+    A.state0 = state0_dev;
+    A.tparams = tparams_dev;
+    A.K = K_dev;
+    A.metrics = metrics_out_dev;
+    A.final_state = final_state_out_dev;
+    A.traj = traj_out_dev;
+    A.feat = feat_out_dev;
+    A.actf = act_out_dev;
+    A.traj_stride = (int)traj_stride;
+    A.traj_slots = (int)traj_slots;
+    A.data_stride = (int)data_stride;
+    A.data_slots = (int)data_slots;
+
+    // K staging: with one episode per thread a block needs at most ceil(T / k_stride) + 1 groups
+    size_t smem = 0;
+    A.k_in_smem = 0;
+    if (chain == 1) {
+        int64_t groups = (kRolloutThreads + k_stride - 1) / k_stride + 1;
+        size_t bytes = (size_t)groups * 4 * k_cols * sizeof(double);
+        if (bytes <= 40 * 1024) {
+            A.k_in_smem = 1;
+            smem = bytes;
+        }
+    }
+    const bool full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 ||
+                      traj_out_dev != nullptr || feat_out_dev != nullptr;
+
+    DeviceGuard guard(ctx->device);
+    cudaError_t err;
+    switch (params->motion_type) {
+    case QT_MOTION_LINEAR: err = launch_motion<QT_MOTION_LINEAR>(*params, A, smem, full, ctx->stream); break;
+    case QT_MOTION_CIRCULAR: err = launch_motion<QT_MOTION_CIRCULAR>(*params, A, smem, full, ctx->stream); break;
+    case QT_MOTION_SINUSOIDAL: err = launch_motion<QT_MOTION_SINUSOIDAL>(*params, A, smem, full, ctx->stream); break;
+    case QT_MOTION_FIGURE8: err = launch_motion<QT_MOTION_FIGURE8>(*params, A, smem, full, ctx->stream); break;
+    default: err = launch_motion<QT_MOTION_STATIONARY>(*params, A, smem, full, ctx->stream); break;
+    }
+    if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "rollout_kernel launch", cudaGetErrorString(err));
+    ctx->launches += 1;
+    return QT_OK;
+}
