@@ -153,9 +153,15 @@ int64_t qt_launch_count(const qt_context *ctx);
 /* ---- A1: QuadcopterEnv.reset(seed) + TargetMotion.reset/_create_pattern ------------------
  * quadcopter_env.py:111-150, target_motion.py:291-369.  One seed per episode; reproduces
  * numpy's default_rng(seed) (SeedSequence -> PCG64 -> uniform / ziggurat standard_normal) on
- * the device.  state_out [12][E], tparams_out [12][E].                                       */
+ * the device.  state_out [12][E], tparams_out [12][E].
+ * draws_io [2][E] (or NULL) carries, per episode, how many raw 64-bit outputs the env stream
+ * (row 0) and the target stream (row 1) have already consumed; it is updated on return.  This
+ * reproduces reset(seed=None), which keeps drawing from the existing generators
+ * (quadcopter_env.py:122-130): pass the counters back in with the same seeds.  NULL = fresh
+ * generators, i.e. reset(seed).                                                              */
 int qt_reset_batched(qt_context *ctx, const qt_params *params, const uint64_t *seeds_dev,
-                     int64_t E, double *state_out_dev, double *tparams_out_dev);
+                     int64_t E, uint64_t *draws_io_dev, double *state_out_dev,
+                     double *tparams_out_dev);
 
 /* Raw generator access for tests: for each seed, n_uniform doubles from Generator.random()
  * followed (same stream) by n_normal draws of standard_normal().  out [n_uniform+n_normal][E]. */
@@ -200,6 +206,10 @@ int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t E, double 
  * episode — tuner semantics, tuning.py:879; chain = E reproduces Evaluator.evaluate, which
  * never resets the controller between episodes, eval.py:198-213).
  *   state0 [12][E], tparams [12][E], K [groups][4][k_cols], metrics_out [16][E],
+ *   ctrl_state_io [4][n_chains] or NULL (n_chains = ceil(E / chain)): LQI integrator (3 rows)
+ *   and saturation count of each chain's controller; read as the initial controller state
+ *   when chain > 1 (Evaluator semantics: whatever state the controller object carries),
+ *   ignored on entry when chain == 1 (reset per episode); always written back on exit,
  *   final_state_out [12][E] or NULL,
  *   traj_out [slots][24][E] or NULL: steps k with k % traj_stride == 0, slot = k / traj_stride,
  *   feat_out f32 [slots][E][18] and act_out f32 [slots][E][4] or NULL (teacher data set,
@@ -207,7 +217,8 @@ int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t E, double 
 int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
                int64_t chain, const double *state0_dev, const double *tparams_dev,
                const double *K_dev, int32_t k_cols, int64_t k_stride, double *metrics_out_dev,
-               double *final_state_out_dev, double *traj_out_dev, int64_t traj_stride,
+               double *ctrl_state_io_dev, double *final_state_out_dev, double *traj_out_dev,
+               int64_t traj_stride,
                int64_t traj_slots, float *feat_out_dev, float *act_out_dev,
                int64_t data_stride, int64_t data_slots);
 

@@ -1,0 +1,31 @@
+"""qtrack-b200: batched closed-loop quadcopter tracking + Riccati-LQR/LQI on NVIDIA B200.
+
+A from-scratch, B200-native implementation of ONE hot path of ``quadcopter_tracking``
+(AgentFoundryExamples/lqr-quadcopter-test): environment reset/step, target motion, the
+Riccati-LQR/LQI control law, evaluation metrics, the controller auto-tuner's candidate evaluation
+and the batched DARE solve that produces the gains — behind the reference's own Python
+interfaces.  All arithmetic runs in hand-written sm_100a CUDA kernels (csrc/, C ABI in
+include/qtrack.h); this package is the thin host layer.  There is no CPU fallback.
+"""
+from .config import (EnvConfig, LoggingParams, QuadcopterParams, SimulationParams, TargetParams)
+from .config import SuccessCriteria as EnvSuccessCriteria
+from .controller import (ACTION_KEYS, BaseController, LQRController, RiccatiLQRController,
+                         build_augmented_lqi_system, build_linearized_system, heuristic_lqr_gain,
+                         solve_dare, solve_dare_batched)
+from .env import BatchedQuadcopterEnv, QuadcopterEnv
+from .eval import Evaluator, load_controller, rollout_device
+from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, format_metrics_report)
+from .tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
+from .dataset import teacher_dataset
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "EnvConfig", "QuadcopterParams", "SimulationParams", "TargetParams", "LoggingParams",
+    "EnvSuccessCriteria", "SuccessCriteria", "QuadcopterEnv", "BatchedQuadcopterEnv",
+    "RiccatiLQRController", "LQRController", "BaseController", "ACTION_KEYS", "solve_dare",
+    "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
+    "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
+    "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",
+    "TuningConfig", "TuningResult", "teacher_dataset",
+]

@@ -151,10 +151,10 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     double *K_dev = reinterpret_cast<double *>(base + off_K);
     QT_CUDA_TRY(ctx, cudaMemcpyAsync(seeds_dev, seeds_host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     QT_CUDA_TRY(ctx, cudaMemcpyAsync(K_dev, K_host, 4 * (size_t)k_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = qt_reset_batched(ctx, params, seeds_dev, E, state_dev, tp_dev);
+    int rc = qt_reset_batched(ctx, params, seeds_dev, E, nullptr, state_dev, tp_dev);
     if (rc) return rc;
     rc = qt_rollout(ctx, params, E, max_steps, chain, state_dev, tp_dev, K_dev, k_cols, E, met_dev, nullptr,
-                    nullptr, 1, 0, nullptr, nullptr, 1, 0);
+                    nullptr, nullptr, 1, 0, nullptr, nullptr, 1, 0);
     if (rc) return rc;
     QT_CUDA_TRY(ctx, cudaMemcpyAsync(metrics_host, met_dev, 16 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     QT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -18,13 +18,17 @@ constexpr int kEnvThreads = 128;
 // and the position offset is the first three uniform doubles of an identical stream.
 __global__ void __launch_bounds__(kEnvThreads)
     reset_kernel(const __grid_constant__ qt_params P, const uint64_t *__restrict__ seeds, int64_t E,
-                 double *__restrict__ state, double *__restrict__ tparams) {
+                 uint64_t *__restrict__ draws, double *__restrict__ state, double *__restrict__ tparams) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const uint64_t seed = seeds[e];
     Pcg64 g_env, g_tgt;
     pcg64_seed(g_env, seed);
     g_tgt = g_env;
+    if (draws) {  // reset(seed=None): resume both streams where the previous reset left them
+        pcg64_advance(g_env, draws[e]);
+        pcg64_advance(g_tgt, draws[E + e]);
+    }
 
     double tp[QT_TARGET_PARAMS];
 #pragma unroll
@@ -104,6 +108,10 @@ __global__ void __launch_bounds__(kEnvThreads)
     for (int i = 3; i < 12; i++) state[(int64_t)i * E + e] = 0.0;
 #pragma unroll
     for (int i = 0; i < QT_TARGET_PARAMS; i++) tparams[(int64_t)i * E + e] = tp[i];
+    if (draws) {
+        draws[e] = g_env.draws;
+        draws[E + e] = g_tgt.draws;
+    }
 }
 
 __global__ void __launch_bounds__(kEnvThreads)
@@ -310,15 +318,16 @@ static inline unsigned grid_for(int64_t E) { return (unsigned)((E + kEnvThreads 
 using namespace qt;
 
 extern "C" int qt_reset_batched(qt_context *ctx, const qt_params *params, const uint64_t *seeds_dev,
-                                int64_t E, double *state_out_dev, double *tparams_out_dev) {
+                                int64_t E, uint64_t *draws_io_dev, double *state_out_dev,
+                                double *tparams_out_dev) {
     if (!ctx) return QT_ERR_ARG;
     QT_REQUIRE(ctx, params && seeds_dev && state_out_dev && tparams_out_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0, "E < 0");
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
     if (E == 0) return QT_OK;
     DeviceGuard guard(ctx->device);
-    reset_kernel<<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, seeds_dev, E, state_out_dev,
-                                                              tparams_out_dev);
+    reset_kernel<<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, seeds_dev, E, draws_io_dev,
+                                                              state_out_dev, tparams_out_dev);
     return check_launch(ctx, "reset_kernel");
 }
 

@@ -6,7 +6,7 @@
 //
 // Both read the [QT_METRICS_DIM][E] array qt_rollout wrote; nothing leaves the device until the
 // caller copies the (tiny) result.  Sums over the episodes of one candidate follow numpy's
-// add.reduce order exactly (first element + pairwise blocks of 128 with 8 accumulators), so a
+// add.reduce order exactly (pairwise blocks of 128 with 8 accumulators), so a
 // candidate's score is bit-identical to the reference's whenever its per-episode metrics are.
 // The evaluation summary is a deterministic two-level tree (no atomics); its sums are
 // re-associated with respect to numpy, the tolerance is stated in DESIGN.md.
@@ -43,7 +43,7 @@ __device__ double np_pairwise(const F &f, int64_t lo, int64_t n) {
 template <typename F>
 __device__ double np_sum(const F &f, int64_t n) {
     if (n <= 0) return 0.0;
-    return f(0) + np_pairwise(f, 1, n - 1);
+    return np_pairwise(f, 0, n);
 }
 
 __global__ void reduce_scores_kernel(const double *__restrict__ metrics, int64_t C, int64_t eps,

@@ -63,6 +63,7 @@ QT_RNG_FN double bits_to_double(uint64_t u) {
 struct Pcg64 {
     unsigned __int128 state;
     unsigned __int128 inc;
+    uint64_t draws;  // raw 64-bit outputs produced so far (lets a caller resume a stream)
 };
 
 QT_RNG_FN uint32_t ss_hashmix(uint32_t value, uint32_t &hash_const) {
@@ -119,9 +120,28 @@ QT_RNG_FN void pcg64_seed(Pcg64 &g, uint64_t seed) {
     g.state = g.state * pcg_mult() + g.inc;
     g.state += initstate;
     g.state = g.state * pcg_mult() + g.inc;
+    g.draws = 0;
+}
+
+// Skip n raw outputs (pcg_advance_lcg_128: O(log n) jump-ahead of the underlying LCG).
+QT_RNG_FN void pcg64_advance(Pcg64 &g, uint64_t n) {
+    unsigned __int128 acc_mult = 1, acc_plus = 0, cur_mult = pcg_mult(), cur_plus = g.inc;
+    uint64_t delta = n;
+    while (delta > 0) {
+        if (delta & 1) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    g.state = acc_mult * g.state + acc_plus;
+    g.draws += n;
 }
 
 QT_RNG_FN uint64_t pcg64_next(Pcg64 &g) {
+    g.draws += 1;
     g.state = g.state * pcg_mult() + g.inc;
     uint64_t hi = (uint64_t)(g.state >> 64), lo = (uint64_t)g.state;
     uint64_t x = hi ^ lo;

@@ -25,7 +25,7 @@ struct RolloutArgs {
     int max_steps;
     int k_in_smem;
     const double *state0, *tparams, *K;
-    double *metrics, *final_state, *traj;
+    double *metrics, *ctrl_state, *final_state, *traj;
     float *feat, *actf;
     int traj_stride, traj_slots, data_stride, data_slots;
 };
@@ -60,6 +60,11 @@ __global__ void __launch_bounds__(kRolloutThreads)
 
     double integ[3] = {0.0, 0.0, 0.0};
     int saturations = 0;
+    if (A.ctrl_state && A.chain > 1) {  // the controller object's state at the time of the call
+#pragma unroll
+        for (int i = 0; i < 3; i++) integ[i] = A.ctrl_state[(int64_t)i * A.n_chains + chain_id];
+        saturations = (int)A.ctrl_state[3 * A.n_chains + chain_id];
+    }
 
     const int64_t first = chain_id * A.chain;
     int64_t last = first + A.chain;
@@ -223,6 +228,11 @@ __global__ void __launch_bounds__(kRolloutThreads)
             for (int i = 0; i < 12; i++) A.final_state[(int64_t)i * E + e] = s[i];
         }
     }
+    if (A.ctrl_state) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) A.ctrl_state[(int64_t)i * A.n_chains + chain_id] = integ[i];
+        A.ctrl_state[3 * A.n_chains + chain_id] = (double)saturations;
+    }
 }
 
 template <int MOTION, bool LQI, bool FULL>
@@ -248,8 +258,9 @@ static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_
 extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
                           int64_t chain, const double *state0_dev, const double *tparams_dev,
                           const double *K_dev, int32_t k_cols, int64_t k_stride,
-                          double *metrics_out_dev, double *final_state_out_dev,
-                          double *traj_out_dev, int64_t traj_stride, int64_t traj_slots,
+                          double *metrics_out_dev, double *ctrl_state_io_dev,
+                          double *final_state_out_dev, double *traj_out_dev, int64_t traj_stride,
+                          int64_t traj_slots,
                           float *feat_out_dev, float *act_out_dev, int64_t data_stride,
                           int64_t data_slots) {
     using namespace qt;
@@ -261,7 +272,6 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     QT_REQUIRE(ctx, (feat_out_dev == nullptr) == (act_out_dev == nullptr), "feat/act must come together");
     if (E == 0) return QT_OK;
     if (chain < 1) chain = 1;
-    if (chain > E) chain = E;
     if (k_stride < 1) k_stride = 1;
     if (traj_stride < 1) traj_stride = 1;
     if (data_stride < 1) data_stride = 1;
@@ -278,6 +288,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     A.tparams = tparams_dev;
     A.K = K_dev;
     A.metrics = metrics_out_dev;
+    A.ctrl_state = ctrl_state_io_dev;
     A.final_state = final_state_out_dev;
     A.traj = traj_out_dev;
     A.feat = feat_out_dev;

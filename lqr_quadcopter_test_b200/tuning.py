@@ -1,0 +1,448 @@
+"""Controller gain auto-tuning on the GPU (drop-in for ``quadcopter_tracking.controllers.tuning``).
+
+The reference evaluates one candidate at a time: build a controller (one scipy DARE), run
+``evaluation_episodes`` episodes step by step, average (tuning.py:846-928).  Here a whole batch of
+candidates is one ``qt_dare_batched`` launch (all Riccati solutions), one ``qt_rollout`` launch
+(candidates x episodes threads, the 64 episodes of a candidate sharing its gain through shared
+memory) and one ``qt_reduce_scores`` launch.  Candidate *generation* stays on the host and
+consumes ``np.random.default_rng(seed)`` in exactly the reference's order (tuning.py:683-735), so
+candidate i here is candidate i there.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+from dataclasses import dataclass, field, fields
+from datetime import datetime, timezone
+from itertools import product
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib
+from . import params as P
+from .config import EnvConfig
+from .controller import LQRController, RiccatiLQRController, heuristic_lqr_gain
+from .metrics import SuccessCriteria
+
+logger = logging.getLogger(__name__)
+
+_VEC3_RANGES = ("kp_pos_range", "ki_pos_range", "kd_pos_range", "ff_velocity_gain_range",
+                "ff_acceleration_gain_range", "q_pos_range", "q_vel_range")
+_SCALAR_RANGES = ("r_thrust_range", "r_rate_range")
+
+
+@dataclass
+class GainSearchSpace:
+    """tuning.py:146-360.  Each ``*_range`` is ``(min_values, max_values)``; None = not searched."""
+
+    kp_pos_range: tuple | None = None
+    ki_pos_range: tuple | None = None
+    kd_pos_range: tuple | None = None
+    ff_velocity_gain_range: tuple | None = None
+    ff_acceleration_gain_range: tuple | None = None
+    q_pos_range: tuple | None = None
+    q_vel_range: tuple | None = None
+    r_thrust_range: tuple | None = None
+    r_rate_range: tuple | None = None
+    r_controls_range: tuple | None = None
+    q_int_range: tuple | None = None
+    use_lqi: bool = False
+
+    @staticmethod
+    def _check_vector(name: str, rng, size: int, labels, what: str) -> None:
+        lo_v, hi_v = rng
+        if len(lo_v) != size or len(hi_v) != size:
+            raise ValueError(f"{name} must have exactly {size} values for [{', '.join(labels)}], "
+                             f"got min={len(lo_v)}, max={len(hi_v)}")
+        for lab, lo, hi in zip(labels, lo_v, hi_v):
+            if lo > hi:
+                raise ValueError(f"{name}[{lab}] has inverted range: min={lo} > max={hi}. "
+                                 f"Swap values or use equal values for fixed parameter.")
+            if lo < 0:
+                raise ValueError(f"{name}[{lab}] has negative minimum: {lo}. {what}")
+
+    def validate(self) -> None:
+        for name in _VEC3_RANGES:
+            rng = getattr(self, name)
+            if rng is not None:
+                self._check_vector(name, rng, 3, ("x", "y", "z"), "Controller gains should be non-negative.")
+        for name in _SCALAR_RANGES:
+            rng = getattr(self, name)
+            if rng is None:
+                continue
+            lo, hi = rng
+            if lo > hi:
+                raise ValueError(f"{name} has inverted range: min={lo} > max={hi}. "
+                                 f"Swap values or use equal values for fixed parameter.")
+            if lo < 0:
+                raise ValueError(f"{name} has negative minimum: {lo}. Cost weights should be non-negative.")
+        if self.r_controls_range is not None:
+            self._check_vector("r_controls_range", self.r_controls_range, 4,
+                               ("thrust", "roll", "pitch", "yaw"), "Cost weights should be non-negative.")
+        if self.q_int_range is not None:
+            self._check_vector("q_int_range", self.q_int_range, 3, ("ix", "iy", "iz"),
+                               "Integral cost weights must be non-negative.")
+
+    def get_active_parameters(self) -> list[str]:
+        return [f.name[: -len("_range")] for f in fields(self)
+                if f.name.endswith("_range") and getattr(self, f.name) is not None]
+
+    @classmethod
+    def from_dict(cls, config: dict) -> "GainSearchSpace":
+        kw = {f.name: config.get(f.name) for f in fields(cls) if f.name != "use_lqi"}
+        return cls(use_lqi=config.get("use_lqi", False), **kw)
+
+    def to_dict(self) -> dict:
+        return {f.name: getattr(self, f.name) for f in fields(self)}
+
+
+@dataclass
+class TuningConfig:
+    """tuning.py:363-478"""
+
+    controller_type: str = "pid"
+    search_space: GainSearchSpace = field(default_factory=GainSearchSpace)
+    strategy: str = "random"
+    max_iterations: int = 50
+    grid_points_per_dim: int = 3
+    evaluation_episodes: int = 5
+    evaluation_horizon: int = 3000
+    seed: int = 42
+    target_motion_type: str = "stationary"
+    episode_length: float = 30.0
+    target_radius: float = 0.5
+    output_dir: str = "reports/tuning"
+    resume_from: str | None = None
+    feedforward_enabled: bool = False
+    cma_sigma0: float = 0.3
+    cma_popsize: int | None = None
+
+    def __post_init__(self) -> None:
+        if self.controller_type not in ("pid", "lqr", "riccati_lqr"):
+            raise ValueError(f"Invalid controller_type: '{self.controller_type}'. "
+                             f"Valid choices are: pid, lqr, riccati_lqr")
+        if self.strategy not in ("grid", "random", "cma_es"):
+            raise ValueError(f"Invalid strategy: '{self.strategy}'. Valid choices are: grid, random, cma_es")
+        if self.max_iterations < 1:
+            raise ValueError(f"max_iterations must be >= 1, got {self.max_iterations}")
+        if self.evaluation_episodes < 1:
+            raise ValueError(f"evaluation_episodes must be >= 1, got {self.evaluation_episodes}")
+        if self.cma_sigma0 <= 0:
+            raise ValueError(f"cma_sigma0 must be > 0, got {self.cma_sigma0}")
+        if self.cma_popsize is not None and self.cma_popsize < 2:
+            raise ValueError(f"cma_popsize must be >= 2, got {self.cma_popsize}")
+
+    @classmethod
+    def from_dict(cls, config: dict) -> "TuningConfig":
+        kw = {f.name: config[f.name] for f in fields(cls) if f.name != "search_space" and f.name in config}
+        return cls(search_space=GainSearchSpace.from_dict(config.get("search_space", {})), **kw)
+
+    def to_dict(self) -> dict:
+        d = {f.name: getattr(self, f.name) for f in fields(self) if f.name != "search_space"}
+        d["search_space"] = self.search_space.to_dict()
+        return d
+
+
+@dataclass
+class TuningResult:
+    """tuning.py:481-578"""
+
+    best_config: dict
+    best_score: float
+    best_metrics: dict
+    all_results: list
+    iterations_completed: int
+    interrupted: bool
+    timestamp: str
+    config: dict
+
+    def to_dict(self) -> dict:
+        return {f.name: getattr(self, f.name) for f in fields(self)}
+
+    @classmethod
+    def from_dict(cls, data: dict) -> "TuningResult":
+        return cls(**{f.name: data[f.name] for f in fields(cls)})
+
+    def save(self, path) -> Path:
+        path = Path(path)
+        _validate_path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(self.to_dict(), f, indent=2)
+        return path
+
+    @classmethod
+    def load(cls, path) -> "TuningResult":
+        path = Path(path)
+        _validate_path(path)
+        if not path.exists():
+            raise FileNotFoundError(f"Tuning results file not found: {path}")
+        if not path.is_file():
+            raise ValueError(f"Path is not a file: {path}")
+        with open(path) as f:
+            return cls.from_dict(json.load(f))
+
+
+def _validate_path(path: Path) -> None:
+    """tuning.py:64-106: refuse traversal sequences and NUL bytes."""
+    text = str(path)
+    if ".." in text:
+        raise ValueError(f"Path contains path traversal sequence '..': {path}. "
+                         "Use absolute paths or paths without parent directory references.")
+    if "\x00" in text:
+        raise ValueError(f"Path contains null byte: {path}")
+
+
+class ControllerTuner:
+    """tuning.py:581-1442 for the Riccati-LQR / LQI (and heuristic LQR) controllers."""
+
+    # candidates evaluated per launch; 65 536 x 64 episodes fits comfortably in 180 GB of HBM
+    max_batch_candidates = 65536
+
+    def __init__(self, config: TuningConfig):
+        self.config = config
+        self.config.search_space.validate()
+        self.rng = np.random.default_rng(config.seed)
+        self.results: list[dict] = []
+        self.best_config: dict = {}
+        self.best_score: float = float("-inf")
+        self.best_metrics: dict = {}
+        self.interrupted: bool = False
+        out = Path(os.environ.get("TUNING_OUTPUT_DIR", config.output_dir))
+        _validate_path(out)
+        self.output_dir = out
+        if config.strategy == "cma_es":
+            try:
+                import cma  # noqa: F401
+            except ImportError:
+                raise ImportError("CMA-ES strategy requires the 'cma' package. Install it with: pip install cma")
+        if config.controller_type == "pid":
+            raise NotImplementedError("PID tuning is outside the accelerated Riccati-LQR/LQI path (DESIGN.md, scope)")
+
+    # -- candidate generation: host, identical RNG consumption to tuning.py:662-735 -----------------
+    def _draw(self, rng_def):
+        lo_v, hi_v = rng_def
+        return [float(self.rng.uniform(lo, hi)) for lo, hi in zip(lo_v, hi_v)]
+
+    def _generate_random_config(self) -> dict:
+        sp = self.config.search_space
+        cfg: dict = {}
+        for key in ("kp_pos", "ki_pos", "kd_pos"):
+            if getattr(sp, key + "_range") is not None:
+                cfg[key] = self._draw(getattr(sp, key + "_range"))
+        for key in ("ff_velocity_gain", "ff_acceleration_gain"):
+            if getattr(sp, key + "_range") is not None:
+                cfg[key] = self._draw(getattr(sp, key + "_range"))
+                cfg["feedforward_enabled"] = True
+        for key in ("q_pos", "q_vel"):
+            if getattr(sp, key + "_range") is not None:
+                cfg[key] = self._draw(getattr(sp, key + "_range"))
+        for key in ("r_thrust", "r_rate"):
+            rng_def = getattr(sp, key + "_range")
+            if rng_def is not None:
+                cfg[key] = float(self.rng.uniform(rng_def[0], rng_def[1]))
+        if sp.r_controls_range is not None:
+            cfg["r_controls"] = self._draw(sp.r_controls_range)
+        if sp.q_int_range is not None:
+            cfg["q_int"] = self._draw(sp.q_int_range)
+            cfg["use_lqi"] = True
+        elif sp.use_lqi:
+            cfg["use_lqi"] = True
+            cfg["q_int"] = [0.0, 0.0, 0.0]
+        return cfg
+
+    def _generate_grid_configs(self) -> list[dict]:
+        """tuning.py:737-830"""
+        sp, n = self.config.search_space, self.config.grid_points_per_dim
+
+        def axis(lo, hi):
+            return [lo] if np.isclose(lo, hi) else list(np.linspace(lo, hi, n))
+
+        grids: dict[str, list] = {}
+        for key in ("kp_pos", "ki_pos", "kd_pos", "ff_velocity_gain", "ff_acceleration_gain", "q_pos", "q_vel"):
+            rng_def = getattr(sp, key + "_range")
+            if rng_def is not None:
+                grids[key] = [list(c) for c in product(*[axis(lo, hi) for lo, hi in zip(*rng_def)])]
+        for key in ("r_thrust", "r_rate"):
+            rng_def = getattr(sp, key + "_range")
+            if rng_def is not None:
+                grids[key] = axis(rng_def[0], rng_def[1])
+        if sp.r_controls_range is not None:
+            grids["r_controls"] = [list(c) for c in product(*[axis(lo, hi) for lo, hi in zip(*sp.r_controls_range)])]
+        if sp.q_int_range is not None:
+            grids["q_int"] = [list(c) for c in product(*[axis(lo, hi) for lo, hi in zip(*sp.q_int_range)])]
+        elif sp.use_lqi:
+            grids["q_int"] = [[0.0, 0.0, 0.0]]
+        if not grids:
+            return []
+        names = list(grids)
+        configs = []
+        for combo in product(*[grids[k] for k in names]):
+            cfg = dict(zip(names, combo))
+            if "ff_velocity_gain" in cfg or "ff_acceleration_gain" in cfg:
+                cfg["feedforward_enabled"] = True
+            if "q_int" in cfg or sp.use_lqi:
+                cfg["use_lqi"] = True
+            configs.append(cfg)
+        return configs
+
+    # -- evaluation ----------------------------------------------------------------------------------
+    def _create_controller(self, controller_config: dict):
+        if self.config.controller_type == "lqr":
+            return LQRController(config=controller_config)
+        if self.config.controller_type == "riccati_lqr":
+            return RiccatiLQRController(config=controller_config)
+        raise ValueError(f"Unknown controller type: {self.config.controller_type}")
+
+    def _env_and_criteria(self):
+        env_config = EnvConfig()
+        env_config.simulation.max_episode_time = self.config.episode_length
+        env_config.target.motion_type = self.config.target_motion_type
+        env_config.success_criteria.target_radius = self.config.target_radius
+        criteria = SuccessCriteria(min_on_target_ratio=0.8, min_episode_duration=self.config.episode_length,
+                                   target_radius=self.config.target_radius)
+        return env_config, criteria
+
+    def _evaluate_config(self, controller_config: dict) -> tuple[float, dict]:
+        """tuning.py:846-928 for one candidate (one controller object, hence one DARE)."""
+        scores, metrics = self.evaluate_configs([controller_config])
+        return scores[0], metrics[0]
+
+    @staticmethod
+    def _batchable(configs: list[dict]) -> bool:
+        """A batch shares one qt_params block, so feedforward gains / LQI mode must agree."""
+        lqi = {bool(c.get("use_lqi", False)) for c in configs}
+        ff = any(c.get("feedforward_enabled", False) for c in configs)
+        return len(lqi) == 1 and not ff
+
+    def evaluate_configs(self, configs: list[dict]) -> tuple[list[float], list[dict]]:
+        """Score every candidate configuration: returns (scores, metrics dictionaries)."""
+        if not configs:
+            return [], []
+        if not self._batchable(configs) or any("Q" in c or "R" in c or "K" in c for c in configs):
+            parts = [self._evaluate_batch([c]) for c in configs]
+            return [p[0][0] for p in parts], [p[1][0] for p in parts]
+        scores, metrics = [], []
+        for i in range(0, len(configs), self.max_batch_candidates):
+            s, m = self._evaluate_batch(configs[i:i + self.max_batch_candidates])
+            scores += s
+            metrics += m
+        return scores, metrics
+
+    def _gains_for(self, configs: list[dict], ctx):
+        """Device gains [C, 4, k_cols] for a batch of candidates + the controller prototype that
+        carries the shared (non-tuned) controller parameters."""
+        import torch
+
+        proto = self._create_controller(configs[0])
+        C = len(configs)
+        if self.config.controller_type == "lqr" or len(configs) == 1:
+            ks = [np.ascontiguousarray(self._create_controller(c).effective_gain()) for c in configs] \
+                if C > 1 else [np.ascontiguousarray(proto.effective_gain())]
+            return torch.as_tensor(np.stack(ks), dtype=torch.float64, device=ctx.device), proto
+        lqi = bool(configs[0].get("use_lqi", False))
+        n = 9 if lqi else 6
+        q = np.empty((C, n))
+        r = np.empty((C, 4))
+        for i, c in enumerate(configs):
+            q[i, 0:3] = c.get("q_pos", [0.0001, 0.0001, 16.0])
+            q[i, 3:6] = c.get("q_vel", [0.0036, 0.0036, 4.0])
+            if lqi:
+                q[i, 6:9] = c.get("q_int", [0.0, 0.0, 0.0])
+            r[i] = c.get("r_controls", [1.0, 1.0, 1.0, 1.0])
+        f64 = dict(dtype=torch.float64, device=ctx.device)
+        qd, rd = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
+        A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
+        Q, R = torch.empty((C, n, n), **f64), torch.empty((C, 4, 4), **f64)
+        ctx.build_lqr_systems(n, C, proto.dt, proto.mass, proto.gravity, qd, rd, A, B, Q, R)
+        K = torch.empty((C, 4, n), **f64)
+        iters = torch.zeros(C, dtype=torch.int32, device=ctx.device)
+        info = torch.zeros(C, dtype=torch.int32, device=ctx.device)
+        ctx.dare_batched(n, 4, C, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
+        bad = torch.nonzero(info != 0).reshape(-1).cpu().tolist()
+        if bad:
+            if lqi:
+                raise RuntimeError(f"DARE failed for {len(bad)} LQI candidates (first: {configs[bad[0]]}); "
+                                   "the reference would fall back to the non-integral heuristic LQR")
+            # riccati_lqr.py:747-777: heuristic LQR built from diag(Q), R[0,0], mean(R[1:,1:])
+            for i in bad:
+                Kf = heuristic_lqr_gain(q[i, 0:3], q[i, 3:6], r[i, 0], float(np.mean(r[i, 1:4])))
+                K[i] = torch.as_tensor(Kf, **f64)
+        self.last_dare_info = info
+        self.last_dare_iters = iters
+        return K, proto
+
+    def _evaluate_batch(self, configs: list[dict]) -> tuple[list[float], list[dict]]:
+        import torch
+
+        ctx = _lib.get_context()
+        ctx.bind_torch_stream()
+        cfg = self.config
+        C, eps = len(configs), cfg.evaluation_episodes
+        env_config, criteria = self._env_and_criteria()
+        K, proto = self._gains_for(configs, ctx)
+        prm = proto.kernel_params(env_config, criteria)
+        lqi = proto.effective_use_lqi()
+        f64 = dict(dtype=torch.float64, device=ctx.device)
+        # every candidate sees the same episode seeds seed + ep (tuning.py:875)
+        seeds = torch.arange(eps, dtype=torch.int64, device=ctx.device) + int(cfg.seed)
+        s0, tp = torch.empty((12, eps), **f64), torch.empty((12, eps), **f64)
+        ctx.reset_batched(prm, seeds, s0, tp)
+        state0 = s0.repeat(1, C).contiguous()
+        tparams = tp.repeat(1, C).contiguous()
+        E = C * eps
+        metrics = torch.empty((16, E), **f64)
+        ctx.rollout(prm, E, int(cfg.evaluation_horizon), 1, state0, tparams, K.contiguous(), 9 if lqi else 6,
+                    eps, metrics)
+        cand = torch.empty((4, C), **f64)
+        ctx.reduce_scores(metrics, C, eps, cand)
+        host = cand.cpu().numpy()
+        self.last_metrics = metrics
+        scores = [float(x) for x in host[0]]
+        out = [{"mean_on_target_ratio": float(host[1, i]), "mean_tracking_error": float(host[2, i]),
+                "success_rate": float(host[3, i]), "episodes_evaluated": eps} for i in range(C)]
+        return scores, out
+
+    # -- search loops ----------------------------------------------------------------------------------
+    def _record_result(self, config: dict, score: float, metrics: dict) -> None:
+        self.results.append({"config": config, "score": score, "metrics": metrics})
+        if score > self.best_score:  # strict: the first of equal scores wins (tuning.py:1084)
+            self.best_score, self.best_config, self.best_metrics = score, config, metrics
+
+    def tune(self) -> TuningResult:
+        """tuning.py:930-982"""
+        cfg = self.config
+        if cfg.resume_from:
+            prev = TuningResult.load(cfg.resume_from)
+            self.results, self.best_config = prev.all_results, prev.best_config
+            self.best_score, self.best_metrics = prev.best_score, prev.best_metrics
+        if cfg.strategy == "grid":
+            configs = self._generate_grid_configs()
+            configs = configs[: min(len(configs), cfg.max_iterations)]
+        elif cfg.strategy == "cma_es":
+            raise NotImplementedError("CMA-ES ask/tell is host bookkeeping outside the accelerated path")
+        else:
+            remaining = cfg.max_iterations - len(self.results)
+            configs = [self._generate_random_config() for _ in range(max(remaining, 0))]
+        scores, metrics = self.evaluate_configs(configs)
+        for c, s, m in zip(configs, scores, metrics):
+            self._record_result(c, s, m)
+        result = TuningResult(
+            best_config=self.best_config, best_score=self.best_score, best_metrics=self.best_metrics,
+            all_results=self.results, iterations_completed=len(self.results), interrupted=self.interrupted,
+            timestamp=datetime.now(timezone.utc).isoformat(), config=cfg.to_dict())
+        self._save_results(result)
+        return result
+
+    def _save_results(self, result: TuningResult) -> None:
+        """tuning.py:1103-1150: timestamped results + a stable "latest" copy."""
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        stamp = datetime.now(timezone.utc).strftime("%Y%m%d_%H%M%S")
+        result.save(self.output_dir / f"tuning_{self.config.controller_type}_{stamp}_results.json")
+        best = {"controller_type": self.config.controller_type,
+                self.config.controller_type: result.best_config,
+                "metrics": result.best_metrics, "score": result.best_score}
+        with open(self.output_dir / f"tuning_{self.config.controller_type}_{stamp}_best_config.json", "w") as f:
+            json.dump(best, f, indent=2)

@@ -12,3 +12,11 @@ extern "C" void rng_probe_host(const uint64_t *seeds, int64_t E, int n_uniform, 
             out[(int64_t)(n_uniform + i) * E + e] = qt::rng_standard_normal(g);
     }
 }
+
+// Skip `skip` raw outputs with the jump-ahead, then draw n doubles.
+extern "C" void rng_resume_host(uint64_t seed, uint64_t skip, int n, double *out) {
+    qt::Pcg64 g;
+    qt::pcg64_seed(g, seed);
+    qt::pcg64_advance(g, skip);
+    for (int i = 0; i < n; i++) out[i] = qt::pcg64_double(g);
+}

@@ -1,0 +1,58 @@
+"""CPU: the multi-rank reduction path with world_size 2 over gloo."""
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+from lqr_quadcopter_test_b200.metrics import SuccessCriteria
+
+
+def _shard_sums(ratios, errs):
+    s = np.zeros(16)
+    n = len(ratios)
+    s[0], s[1], s[2], s[3], s[4] = n, (ratios >= 0.8).sum(), ratios.sum(), errs.sum(), 10.0 * n
+    s[5], s[6] = ((ratios - ratios.mean()) ** 2).sum(), ((errs - errs.mean()) ** 2).sum()
+    s[7], s[8], s[9], s[10] = ratios.max(), np.argmax(ratios), ratios.min(), np.argmin(ratios)
+    return s
+
+
+def _worker(rank, size, port, total, out_q):
+    import os
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(size), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from lqr_quadcopter_test_b200 import dist as qd
+
+    qd.init_process_group("gloo")
+    rng = np.random.default_rng(0)
+    ratios, errs = np.round(rng.uniform(0.5, 1, total), 2), rng.uniform(0, 1, total)
+    lo, hi = qd.shard_range(total, rank, size)
+    local = torch.from_numpy(_shard_sums(ratios[lo:hi], errs[lo:hi]))
+    summary, merged = qd.reduce_summary_across_ranks(local, lo, SuccessCriteria())
+    # tuning: per-candidate rows of unequal shard widths
+    C = 11
+    clo, chi = qd.shard_range(C, rank, size)
+    cand = torch.arange(4 * C, dtype=torch.float64).reshape(4, C)[:, clo:chi].contiguous()
+    full = qd.gather_candidate_scores(cand, C)
+    out_q.put((rank, summary.mean_on_target_ratio, summary.std_on_target_ratio, summary.best_episode_idx,
+               summary.worst_episode_idx, summary.total_episodes, full.numpy().tolist()))
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_reduction_matches_single_process():
+    total, size, port = 1001, 2, 29731
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, total, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(size)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    ratios = np.round(rng.uniform(0.5, 1, total), 2)
+    for _rank, mean, std, best, worst, n, full in results:
+        assert n == total
+        assert abs(mean - ratios.mean()) < 1e-13 and abs(std - ratios.std()) < 1e-12
+        assert best == int(np.argmax(ratios)) and worst == int(np.argmin(ratios))
+        assert full == torch.arange(44, dtype=torch.float64).reshape(4, 11).numpy().tolist()

@@ -1,0 +1,201 @@
+"""CPU: host-side logic of the drop-in layer (no kernel launches)."""
+import math
+
+import numpy as np
+import pytest
+
+from lqr_quadcopter_test_b200 import params as P
+from lqr_quadcopter_test_b200.config import EnvConfig
+from lqr_quadcopter_test_b200.controller import (build_augmented_lqi_system, build_linearized_system,
+                                                 heuristic_lqr_gain, observation_to_vector)
+from lqr_quadcopter_test_b200.dist import shard_range
+from lqr_quadcopter_test_b200.metrics import (EpisodeMetricsView, SuccessCriteria, episode_metrics_from_vector,
+                                              merge_summary_sums, summary_from_sums)
+from lqr_quadcopter_test_b200.tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
+
+
+def test_env_config_round_trip_and_legacy_keys():
+    cfg = EnvConfig.from_dict({"dt": 0.02, "episode_length": 12.0, "seed": 7,
+                               "target": {"motion_type": "circular", "radius_requirement": 0.3, "center": [1, 2, 3]},
+                               "quadcopter": {"mass": 1.5, "unknown_key": 1}})
+    assert cfg.simulation.dt == 0.02 and cfg.simulation.max_episode_time == 12.0 and cfg.seed == 7
+    assert cfg.success_criteria.target_radius == 0.3 and cfg.target.center == (1, 2, 3)
+    assert cfg.quadcopter.mass == 1.5
+    again = EnvConfig.from_dict(cfg.to_dict())
+    assert again.to_dict() == cfg.to_dict()
+    assert EnvConfig().to_dict()["simulation"]["integrator"] == "rk4"
+
+
+def test_make_params_flattens_configuration():
+    cfg = EnvConfig()
+    cfg.target.motion_type = "Sinusoidal"
+    cfg.simulation.integrator = "euler"
+    p = P.make_params(cfg, None, SuccessCriteria(0.7, 20.0, 0.4))
+    assert p.motion_type == 3 and p.integrator == 1
+    assert (p.crit_min_on_target_ratio, p.crit_min_episode_duration, p.crit_target_radius) == (0.7, 20.0, 0.4)
+    cfg.target.motion_type = "zigzag"
+    with pytest.raises(ValueError, match="Invalid motion type"):
+        P.make_params(cfg)
+
+
+def test_design_matrices(golden):
+    g = golden["dare"]
+    A, B = build_linearized_system(0.01)
+    np.testing.assert_array_equal(A, g["lqr_default_A"])
+    np.testing.assert_array_equal(B, g["lqr_default_B"])
+    A9, B9 = build_augmented_lqi_system(A, B, 0.01)
+    np.testing.assert_array_equal(A9, g["lqi_default_A"])
+    np.testing.assert_array_equal(B9, g["lqi_default_B"])
+    K = heuristic_lqr_gain([1e-4, 1e-4, 16.0], [3.6e-3, 3.6e-3, 4.0], 1.0, 1.0)
+    assert K.shape == (4, 6) and K[0, 2] == 4.0 and K[1, 1] == -0.01 and K[2, 0] == 0.01 and not K[3].any()
+
+
+def test_observation_vector_layout():
+    obs = {"quadcopter": {"position": [1, 2, 3], "velocity": [4, 5, 6], "attitude": [7, 8, 9],
+                          "angular_velocity": [10, 11, 12]},
+           "target": {"position": [13, 14, 15], "velocity": [16, 17, 18]}, "time": 0.5}
+    v = observation_to_vector(obs)
+    assert v.shape == (22,) and list(v[:18]) == list(range(1, 19)) and not v[18:21].any() and v[21] == 0.5
+
+
+def test_search_space_validation_messages():
+    GainSearchSpace(q_pos_range=([0, 0, 0], [1, 1, 1])).validate()
+    with pytest.raises(ValueError, match="inverted range"):
+        GainSearchSpace(q_pos_range=([2, 0, 0], [1, 1, 1])).validate()
+    with pytest.raises(ValueError, match="negative minimum"):
+        GainSearchSpace(q_vel_range=([-1, 0, 0], [1, 1, 1])).validate()
+    with pytest.raises(ValueError, match="exactly 4 values"):
+        GainSearchSpace(r_controls_range=([1, 1, 1], [2, 2, 2])).validate()
+    with pytest.raises(ValueError, match="exactly 3 values"):
+        GainSearchSpace(q_int_range=([0, 0], [1, 1])).validate()
+    sp = GainSearchSpace(q_pos_range=([0] * 3, [1] * 3), r_controls_range=([1] * 4, [2] * 4))
+    assert sp.get_active_parameters() == ["q_pos", "r_controls"]
+    assert GainSearchSpace.from_dict(sp.to_dict()) == sp
+
+
+def test_tuning_config_validation():
+    with pytest.raises(ValueError, match="Invalid controller_type"):
+        TuningConfig(controller_type="mpc")
+    with pytest.raises(ValueError, match="Invalid strategy"):
+        TuningConfig(strategy="bayes")
+    with pytest.raises(ValueError, match="max_iterations"):
+        TuningConfig(max_iterations=0)
+    tc = TuningConfig(controller_type="riccati_lqr", max_iterations=3)
+    assert TuningConfig.from_dict(tc.to_dict()).to_dict() == tc.to_dict()
+
+
+def _riccati_space(lqi=False):
+    kw = dict(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), q_vel_range=([1e-3, 1e-3, 2.0], [1e-2, 1e-2, 8.0]),
+              r_controls_range=([0.5] * 4, [2.0] * 4))
+    if lqi:
+        kw["q_int_range"] = ([1e-6, 1e-6, 1e-4], [1e-5, 1e-5, 1e-2])
+    return GainSearchSpace(**kw)
+
+
+@pytest.mark.parametrize("lqi", [False, True])
+def test_random_candidates_consume_the_rng_like_the_reference(golden, lqi, tmp_path):
+    g = golden["tuning"]
+    key = "riccati_lqi_stationary" if lqi else "riccati_stationary"
+    tuner = ControllerTuner(TuningConfig(controller_type="riccati_lqr", search_space=_riccati_space(lqi), seed=42,
+                                         output_dir=str(tmp_path)))
+    cfgs = [tuner._generate_random_config() for _ in range(5)]
+    q = np.array([c["q_pos"] + c["q_vel"] + (c["q_int"] if lqi else []) for c in cfgs])
+    r = np.array([c["r_controls"] for c in cfgs])
+    np.testing.assert_array_equal(q, g[key + "_q"])
+    np.testing.assert_array_equal(r, g[key + "_r"])
+    assert all(c.get("use_lqi", False) == lqi for c in cfgs)
+
+
+def test_grid_candidates_match_the_reference(golden, tmp_path):
+    g = golden["tuning"]
+    tc = TuningConfig(controller_type="riccati_lqr", strategy="grid", grid_points_per_dim=2, max_iterations=10,
+                      output_dir=str(tmp_path),
+                      search_space=GainSearchSpace(q_pos_range=([1e-4, 1e-4, 10.0], [1e-4, 2e-4, 20.0]),
+                                                   r_controls_range=([1.0] * 4, [1.0, 1.0, 1.0, 2.0])))
+    grid = ControllerTuner(tc)._generate_grid_configs()
+    np.testing.assert_array_equal(np.array([c["q_pos"] for c in grid]), g["grid_q_pos"])
+    np.testing.assert_array_equal(np.array([c["r_controls"] for c in grid]), g["grid_r_controls"])
+
+
+def test_tuner_rejects_what_is_out_of_scope(tmp_path):
+    with pytest.raises(NotImplementedError):
+        ControllerTuner(TuningConfig(controller_type="pid", output_dir=str(tmp_path)))
+    with pytest.raises(ImportError, match="cma"):
+        ControllerTuner(TuningConfig(controller_type="riccati_lqr", strategy="cma_es", output_dir=str(tmp_path)))
+    with pytest.raises(ValueError, match="traversal"):
+        ControllerTuner(TuningConfig(controller_type="riccati_lqr", output_dir="../evil"))
+
+
+def test_tuning_result_round_trip(tmp_path):
+    r = TuningResult({"a": 1}, 0.5, {"m": 2}, [{"config": {}, "score": 0.5, "metrics": {}}], 1, False, "t", {})
+    path = r.save(tmp_path / "res.json")
+    assert TuningResult.load(path).to_dict() == r.to_dict()
+    with pytest.raises(FileNotFoundError):
+        TuningResult.load(tmp_path / "missing.json")
+
+
+def test_episode_metrics_from_vector_and_view(golden):
+    g = golden["rollouts"]
+    M = g["lqr_linear_metrics"]
+    extra = g["lqr_linear_extra"]
+    view = EpisodeMetricsView(M)
+    assert len(view) == M.shape[1]
+    for i, m in enumerate(view):
+        assert m.on_target_ratio == extra[0, i]
+        assert abs(m.mean_tracking_error - extra[1, i]) < 1e-15
+        assert abs(m.rms_tracking_error - extra[2, i]) < 1e-15
+        assert abs(m.mean_control_effort - extra[3, i]) < 1e-13
+        assert m.termination_reason == "time_limit" and m.episode_duration >= 30.0
+    empty = episode_metrics_from_vector(np.zeros(16))
+    assert empty.termination_reason == "no_data" and not empty.success
+
+
+def _sums_of(ratios, errs, effort, succ, offset=0):
+    n = len(ratios)
+    s = np.zeros(16)
+    s[0], s[1], s[2], s[3], s[4] = n, succ.sum(), ratios.sum(), errs.sum(), effort.sum()
+    s[5], s[6] = ((ratios - ratios.mean()) ** 2).sum(), ((errs - errs.mean()) ** 2).sum()
+    s[7], s[8], s[9], s[10] = ratios.max(), np.argmax(ratios), ratios.min(), np.argmin(ratios)
+    return s
+
+
+def test_merge_of_shard_sums_equals_numpy_on_the_whole():
+    rng = np.random.default_rng(3)
+    n = 1000
+    ratios = np.round(rng.uniform(0.5, 1.0, n), 2)  # ties on purpose
+    errs, effort, succ = rng.uniform(0, 1, n), rng.uniform(9, 11, n), (ratios >= 0.8).astype(float)
+    cuts = [0, 137, 600, 601, 1000]
+    parts = [_sums_of(ratios[a:b], errs[a:b], effort[a:b], succ[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    merged = merge_summary_sums(parts, cuts[:-1])
+    s = summary_from_sums(merged, SuccessCriteria(), [])
+    assert s.total_episodes == n and s.successful_episodes == int(succ.sum())
+    assert math.isclose(s.mean_on_target_ratio, ratios.mean(), rel_tol=1e-13)
+    assert math.isclose(s.std_on_target_ratio, ratios.std(), rel_tol=1e-11)
+    assert math.isclose(s.std_tracking_error, errs.std(), rel_tol=1e-11)
+    assert s.best_episode_idx == int(np.argmax(ratios)) and s.worst_episode_idx == int(np.argmin(ratios))
+    assert s.meets_criteria == (ratios.mean() >= 0.8)
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 64, 65536, 1_000_003):
+        for size in (1, 2, 3, 8):
+            spans = [shard_range(total, r, size) for r in range(size)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            widths = [hi - lo for lo, hi in spans]
+            assert max(widths) - min(widths) <= 1
+
+
+def test_controller_configuration_errors_come_before_any_gpu_work():
+    from lqr_quadcopter_test_b200 import RiccatiLQRController
+
+    with pytest.raises(ValueError, match="q_int must have exactly 3 elements"):
+        RiccatiLQRController(config={"use_lqi": True, "q_int": [0.1, 0.2]})
+    with pytest.raises(ValueError, match="non-negative"):
+        RiccatiLQRController(config={"use_lqi": True, "q_int": [0.1, -0.2, 0.1]})
+    with pytest.raises(ValueError, match="q_pos must have 3 elements"):
+        RiccatiLQRController(config={"q_pos": [1, 2]})
+    with pytest.raises(ValueError, match=r"R matrix must have shape \(4, 4\)"):
+        RiccatiLQRController(config={"R": np.eye(3)})
+    with pytest.raises(ValueError, match=r"Q matrix must have shape \(6, 6\)"):
+        RiccatiLQRController(config={"Q": np.eye(5)})
