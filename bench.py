@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""Headline benchmark: closed-loop env-steps/s of the fused rollout (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on host cores
+
+One "step" = one pass of the hot path over one batch: 2^20 episodes per GPU, linear target,
+Riccati-LQR default gains, 3000 env steps of dt = 0.01 each (30 s episodes), followed by the
+evaluation-summary reduction (and, for N > 1, the one all_gather of 17 doubles per rank).  Weak
+scaling: every rank gets its own 2^20 episodes (seeds disjoint).  Prints ONE JSON line.
+
+  value      env-steps/s over all ranks, initial conditions already resident in HBM
+  e2e        the same pass through the host-buffer C-ABI call (qt_evaluate_host): pinned host seeds
+             in, H2D, reset kernel, rollout kernel, D2H of the [16, E] metric array out
+  roofline   rollout kernel vs the FP64 pipe: 440 algorithmic flops per env step
+             over the kernel's CUDA-event duration, against a DFMA peak probed in this same run
+             (MEASURED_PEAKS.json has no FP64 figure); HBM numbers are given for context
+  cpu_baseline  the CPU oracle (C restatement of the reference's loop, all host threads) on a bounded
+             sample of the same workload — a reported baseline, not the optimisation target
+  dare       batched DARE throughput (second headline metric): 65 536 n=6 systems per launch
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+EPISODES_PER_GPU = 1 << 20
+STEPS_PER_EPISODE = 3000
+FLOPS_PER_ENV_STEP = 440.0           # LQR, linear target, RK4
+DARE_BATCH = 65536
+DARE_N = 6
+METRIC = "closed-loop env-steps/s (Riccati-LQR, linear target, 30 s episodes at dt=0.01)"
+
+
+def w_dare(n: int, m: int, k: float) -> float:
+    """canonical flop count of one SDA solve with k doubling iterations."""
+    return k * (50.0 / 3.0) * n ** 3 + (4 * n * n * m + 2 * n * m * m + (2.0 / 3.0) * m ** 3 + 2 * m * m * n)
+
+
+def workload_config(n_gpus: int, episodes: int) -> dict:
+    return {
+        "workload": "BASELINE configs[1]: 2^20 parallel episodes per GPU, linear target motion, Riccati-LQR "
+                    "default gains, 30 s at dt=0.01 (3000 env steps per episode), reset(seed=42+i)",
+        "episodes_per_gpu": episodes,
+        "steps_per_episode": STEPS_PER_EPISODE,
+        "parallelism": f"episodes sharded over {n_gpus} GPU(s), no data-path collective",
+        "l2_policy": "inputs exceed L2: 24 fp64 initial-condition rows x 2^20 episodes = 201 MB read per pass "
+                     "(> 126 MB L2); the kernel is register-resident and FP64-bound, cache state is immaterial",
+    }
+
+
+# ----------------------------------------------------------------------------- clock sampling --
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, sm_max, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    sm_max.append(float(parts[1]))
+                    power.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        except OSError:
+            pass
+        finally:
+            if self.path and os.path.exists(self.path):
+                os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(sm_max), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline --
+def cpu_port_rate(episodes: int, n_threads: int, max_steps: int = STEPS_PER_EPISODE):
+    """Time the oracle (oracle/qt_oracle.c) on `episodes` linear-target episodes; returns
+    (env-steps/s, seconds).  Initial conditions come from numpy exactly as the reference draws them."""
+    import numpy as np
+
+    import oracle
+    from lqr_quadcopter_test_b200 import params as P
+    from lqr_quadcopter_test_b200.config import EnvConfig
+
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    prm = P.make_params(env)
+    A, B = oracle.build_systems_reference()
+    _, K = oracle.solve_dare_reference(A, B, np.diag([1e-4, 1e-4, 16.0, 3.6e-3, 3.6e-3, 4.0]), np.eye(4))
+    s0, tp = oracle.reset_reference(prm, np.arange(42, 42 + episodes))
+    t0 = time.perf_counter()
+    out = oracle.rollout(prm, s0, tp, K, max_steps=max_steps + 2, n_threads=n_threads, want_final_state=False)
+    dt = time.perf_counter() - t0
+    steps = float(out["metrics"][0].sum())
+    return steps / dt, dt
+
+
+def sized_cpu_sample(target_seconds: float, n_threads: int) -> int:
+    rate, _ = cpu_port_rate(max(2 * n_threads, 16), n_threads, max_steps=600)
+    episodes = int(rate * target_seconds / STEPS_PER_EPISODE)
+    return max(n_threads, min(episodes, 1 << 16))
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    episodes = sized_cpu_sample(6.0, cores)
+    for _ in range(args.warmup):
+        cpu_port_rate(max(cores, episodes // 8), cores)
+    t_total, steps_total = 0.0, 0.0
+    for _ in range(args.steps):
+        rate, dt = cpu_port_rate(episodes, cores)
+        t_total += dt
+        steps_total += rate * dt
+    value = steps_total / t_total
+    sample = (f"{episodes} of the 2^20 episodes per step ({episodes * STEPS_PER_EPISODE} env steps), "
+              f"{cores} host threads, C port of the reference's loop (oracle/qt_oracle.c, -O2, no FMA contraction)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, EPISODES_PER_GPU),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "The reference itself is single-threaded Python (~4.5e3 env-steps/s/core, BASELINE.md); it cannot "
+                "travel to the GPU box, so this arm times its C restatement, a far stronger CPU baseline.",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- GPU arm --
+def run_gpu_arm(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lqr_quadcopter_test_b200 import RiccatiLQRController, SuccessCriteria, _lib
+    from lqr_quadcopter_test_b200 import dist as qd
+    from lqr_quadcopter_test_b200.config import EnvConfig
+
+    rank, world, local = qd.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: qtrack has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    ctx = _lib.get_context(local)
+    dev = ctx.device
+    E = args.episodes
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    ctrl = RiccatiLQRController(config={})
+    prm = ctrl.kernel_params(env, SuccessCriteria())
+    K = torch.as_tensor(np.ascontiguousarray(ctrl.K), dtype=torch.float64, device=dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+    seeds = torch.arange(E, dtype=torch.int64, device=dev) + 42 + rank * E
+    state0, tparams = torch.empty((12, E), **f64), torch.empty((12, E), **f64)
+    metrics, sums = torch.empty((16, E), **f64), torch.zeros(16, **f64)
+    ctx.reset_batched(prm, seeds, state0, tparams)
+    max_steps = STEPS_PER_EPISODE + 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_ms: list[float] = []
+
+    def one_pass(timed: bool):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ctx.rollout(prm, E, max_steps, 1, state0, tparams, K, 6, E, metrics)
+        ev1.record()
+        ctx.reduce_summary(metrics, E, sums)
+        if world > 1:
+            qd.reduce_summary_across_ranks(sums, rank * E)
+        if timed:
+            kernel_events.append((ev0, ev1))
+
+    kernel_events: list = []
+    for _ in range(args.warmup):
+        one_pass(False)
+    barrier()
+    launches0 = ctx.launches
+    with ClockSampler(local) as clocks:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            one_pass(True)
+        t1.record()
+        barrier()
+        elapsed_ms = t0.elapsed_time(t1)
+    gpu_launches = ctx.launches - launches0
+    clock_info = clocks.summary()
+    kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
+    total_steps_rank = float(metrics[0].sum().item()) * args.steps
+    el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([total_steps_rank], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    elapsed_ms, total_steps = float(el.item()), float(tot.item())
+    value = total_steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (H2D seeds, reset, rollout, D2H metrics) -------------
+    seeds_host = (torch.arange(E, dtype=torch.int64) + 42 + rank * E).pin_memory()
+    K_host = torch.as_tensor(np.ascontiguousarray(ctrl.K), dtype=torch.float64).pin_memory()
+    metrics_host = torch.empty((16, E), dtype=torch.float64).pin_memory()
+    ctx.evaluate_host(prm, seeds_host, max_steps, 1, K_host, 6, metrics_host)  # warm-up (allocates scratch)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.evaluate_host(prm, seeds_host, max_steps, 1, K_host, 6, metrics_host)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = float(metrics_host[0].sum().item()) * e2e_steps * world / float(e2e_t.item())
+    same = bool(torch.equal(metrics_host, metrics.cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 only: roofline denominators, DARE throughput, CPU baseline --------------------------
+    fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
+    k_ms = statistics.mean(kernel_ms)
+    steps_per_launch = float(metrics[0].sum().item())
+    achieved = steps_per_launch * FLOPS_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    algo_bytes = (24 + 16) * 8.0 * E
+    roofline = {
+        "bound": "fp64", "kernel": "rollout_kernel<linear, LQR, lean>", "achieved": achieved, "peak": fp64_tflops,
+        "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops > 0 else None, "traffic": None,
+        "peak_source": "register-resident DFMA probe (qt_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
+        "algorithmic_flops_per_env_step": FLOPS_PER_ENV_STEP, "kernel_ms": k_ms,
+        "kernel_share_of_step": k_ms * args.steps / elapsed_ms if world == 1 else None,
+        "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (k_ms * 1e-3) / 1e9,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+
+    # DARE: 65 536 candidates of the n=6 design (tuning_riccati.yaml ranges), matrices resident
+    rng = np.random.default_rng(42)
+    q = rng.uniform([5e-5, 5e-5, 10, 1e-3, 1e-3, 2], [5e-4, 5e-4, 25, 1e-2, 1e-2, 8], (DARE_BATCH, 6))
+    r = rng.uniform(0.5, 2.0, (DARE_BATCH, 4))
+    qd_, rd_ = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
+    A, B = torch.empty((6, 6), **f64), torch.empty((6, 4), **f64)
+    Q, R = torch.empty((DARE_BATCH, 6, 6), **f64), torch.empty((DARE_BATCH, 4, 4), **f64)
+    ctx.build_lqr_systems(6, DARE_BATCH, 0.01, 1.0, 9.81, qd_, rd_, A, B, Q, R)
+    Kd = torch.empty((DARE_BATCH, 4, 6), **f64)
+    iters = torch.zeros(DARE_BATCH, dtype=torch.int32, device=dev)
+    info = torch.zeros(DARE_BATCH, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ctx.dare_batched(6, 4, DARE_BATCH, A, 0, B, 0, Q, 36, R, 16, None, Kd, iters, info)
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    d0.record()
+    for _ in range(reps):
+        ctx.dare_batched(6, 4, DARE_BATCH, A, 0, B, 0, Q, 36, R, 16, None, Kd, iters, info)
+    d1.record()
+    torch.cuda.synchronize()
+    dare_ms = d0.elapsed_time(d1) / reps
+    mean_iters = float(iters.double().mean().item())
+    dare_rate = DARE_BATCH / (dare_ms * 1e-3)
+    dare_tflops = dare_rate * w_dare(DARE_N, 4, mean_iters) / 1e12
+    dare = {"metric": "batched DARE solves/s (n=6, m=4, validation + solve + gain)", "value": dare_rate,
+            "unit": "solves/s", "batch": DARE_BATCH, "ms_per_launch": dare_ms, "mean_doubling_iterations": mean_iters,
+            "failed": int((info != 0).sum().item()),
+            "roofline": {"bound": "fp64", "achieved": dare_tflops, "peak": fp64_tflops, "unit": "TFLOP/s",
+                         "frac": dare_tflops / fp64_tflops if fp64_tflops > 0 else None,
+                         "flops_per_solve": w_dare(DARE_N, 4, mean_iters)}}
+
+    cores = os.cpu_count() or 1
+    sample_eps = sized_cpu_sample(10.0, cores)
+    cpu_rate, cpu_s = cpu_port_rate(sample_eps, cores)
+    cpu1_rate, _ = cpu_port_rate(max(8, sample_eps // (4 * cores)), 1)
+    cpu_baseline = {
+        "value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+        "sample": f"{sample_eps} of the 2^20 episodes x 3000 steps ({cpu_s:.1f} s), oracle/qt_oracle.c on {cores} threads",
+        "single_core_value": cpu1_rate,
+        "python_reference_note": "the Python reference measured 4.5e3 env-steps/s on one core (BASELINE.md §2)",
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, E),
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * E + 4 * 6 * 8,
+                "d2h_bytes_per_step": 16 * 8 * E, "api": "qt_evaluate_host (C ABI, pinned host buffers)",
+                "matches_device_resident_result": same},
+        "gpu_launches": int(gpu_launches),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["qtrack", "reference"], default="qtrack")
+    ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU (default 2^20)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

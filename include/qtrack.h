@@ -142,8 +142,9 @@ void qt_params_default(qt_params *p);
 int qt_create(int device, qt_context **out);
 void qt_destroy(qt_context *ctx);
 const char *qt_last_error(const qt_context *ctx);
-/* Use an existing CUDA stream (cudaStream_t as void*, e.g. torch.cuda.current_stream().cuda_stream);
-   NULL selects the context's own non-blocking stream. */
+/* Enqueue on an existing CUDA stream (cudaStream_t as void*, e.g. torch.cuda.current_stream().cuda_stream).
+   NULL means CUDA's legacy default stream (what torch uses by default).  Until the first call a
+   context uses a private non-blocking stream of its own. */
 int qt_set_stream(qt_context *ctx, void *cuda_stream);
 void *qt_get_stream(const qt_context *ctx);
 int qt_synchronize(qt_context *ctx);

@@ -107,7 +107,8 @@ extern "C" const char *qt_last_error(const qt_context *ctx) { return ctx ? ctx->
 
 extern "C" int qt_set_stream(qt_context *ctx, void *cuda_stream) {
     if (!ctx) return QT_ERR_ARG;
-    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    // NULL is a real stream: CUDA's legacy default stream, which is what torch uses unless told otherwise
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     return QT_OK;
 }
 

