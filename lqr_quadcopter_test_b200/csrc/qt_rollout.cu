@@ -19,6 +19,9 @@
 namespace qt {
 
 constexpr int kRolloutThreads = 128;
+#ifndef QT_ROLLOUT_MIN_BLOCKS
+#define QT_ROLLOUT_MIN_BLOCKS 1  // resident blocks per SM the register allocator must allow
+#endif
 
 struct RolloutArgs {
     int64_t E, n_chains, chain, k_stride;
@@ -31,7 +34,7 @@ struct RolloutArgs {
 };
 
 template <int MOTION, bool LQI, bool FULL>
-__global__ void __launch_bounds__(kRolloutThreads)
+__global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ RolloutArgs A) {
     extern __shared__ double sK[];
     constexpr int KC = LQI ? 9 : 6;
