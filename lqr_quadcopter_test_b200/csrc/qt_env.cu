@@ -130,8 +130,9 @@ template <int MOTION>
 __device__ __forceinline__ void observe_one(const qt_params &P, int64_t E, int64_t e,
                                             const double *state, double t, const double *tparams,
                                             double *obs) {
-    TargetGen<MOTION> tg;
-    tg.load(tparams, E, e);
+    TargetGen<MOTION, 1> tg;
+    double par[QT_TARGET_PARAMS];
+    tg.load(par, tparams, E, e);
     double p[3], v[3], a[3];
     tg.template state<true>(P, t, p, v, a);
 #pragma unroll
@@ -225,8 +226,9 @@ __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, 
     double s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = A.state[(int64_t)i * E + e];
-    TargetGen<MOTION> tg;
-    tg.load(A.tparams, E, e);
+    TargetGen<MOTION, 1> tg;
+    double par[QT_TARGET_PARAMS];
+    tg.load(par, A.tparams, E, e);
     double t = A.time[e];
     double tp[3], tv[3], ta[3], act[4], actv[4];
     if (A.action_in) {
@@ -252,9 +254,9 @@ __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, 
     DynConsts C;
     C.init(P);
     if (P.integrator == QT_INTEGRATOR_EULER)
-        integrate_euler(C, P.dt, s, actv);
+        integrate<true>(C, s, actv);
     else
-        integrate_rk4(C, P.dt, s, actv);
+        integrate<false>(C, s, actv);
     constrain_state(P, C, s);
     t += P.dt;
     tg.template state<true>(P, t, tp, tv, ta);

@@ -20,45 +20,55 @@ namespace qt {
 
 constexpr int kRolloutThreads = 128;
 #ifndef QT_ROLLOUT_MIN_BLOCKS
-#define QT_ROLLOUT_MIN_BLOCKS 1  // resident blocks per SM the register allocator must allow
+#define QT_ROLLOUT_MIN_BLOCKS 4  // resident blocks per SM the register allocator must allow (128 registers)
 #endif
 
 struct RolloutArgs {
     int64_t E, n_chains, chain, k_stride;
     int max_steps;
     int k_in_smem;
+    int k_smem_doubles;  // doubles reserved for the staged gains at the start of shared memory
     const double *state0, *tparams, *K;
     double *metrics, *ctrl_state, *final_state, *traj;
     float *feat, *actf;
     int traj_stride, traj_slots, data_stride, data_slots;
 };
 
+// Per-thread values that are touched once per step (metric accumulators, target-pattern
+// parameters) live in this thread's column of a shared-memory tile instead of registers: the
+// integrator needs ~110 registers at its widest point, and keeping the cold state out of the
+// register file is what lets four 128-thread blocks (16 warps) stay resident per SM without
+// spilling.  Column access (row * blockDim + threadIdx) is conflict free.
+enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_MAX_ERR, CR_OV_CUR, CR_OV_MAX, CR_TARGET };
+constexpr int kColdRows = CR_TARGET + QT_TARGET_PARAMS;
+
 template <int MOTION, bool LQI, bool FULL>
 __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
-    rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ RolloutArgs A) {
-    extern __shared__ double sK[];
+    rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
+                   const __grid_constant__ RolloutArgs A) {
+    extern __shared__ double smem[];
     constexpr int KC = LQI ? 9 : 6;
+    constexpr int T = kRolloutThreads;
     const int64_t E = A.E;
-    const int64_t chain_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t chain_id = (int64_t)blockIdx.x * T + threadIdx.x;
+    double *sK = smem;
+    double *cold = smem + A.k_smem_doubles + threadIdx.x;  // this thread's column: cold[row * T]
 
     int64_t g0 = 0;
     if (A.k_in_smem) {
         // chain == 1 here: the block covers episodes [b*T, b*T+T)
-        const int64_t ep0 = (int64_t)blockIdx.x * blockDim.x;
-        int64_t ep1 = ep0 + blockDim.x - 1;
+        const int64_t ep0 = (int64_t)blockIdx.x * T;
+        int64_t ep1 = ep0 + T - 1;
         if (ep1 > E - 1) ep1 = E - 1;
         g0 = ep0 / A.k_stride;
         const int64_t g1 = ep1 / A.k_stride;
         const int n = (int)(g1 - g0 + 1) * 4 * KC;
         const double *src = A.K + g0 * 4 * KC;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sK[i] = src[i];
+        for (int i = threadIdx.x; i < n; i += T) sK[i] = src[i];
         __syncthreads();
     }
     if (chain_id >= A.n_chains) return;
 
-    DynConsts C;
-    C.init(P);
-    const double dt = P.dt;
     const bool euler = FULL && (P.integrator == QT_INTEGRATOR_EULER);
 
     double integ[3] = {0.0, 0.0, 0.0};
@@ -77,8 +87,8 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         double s[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = A.state0[(int64_t)i * E + e];
-        TargetGen<MOTION> tg;
-        tg.load(A.tparams, E, e);
+        TargetGen<MOTION, T> tg;
+        tg.load(cold + CR_TARGET * T, A.tparams, E, e);
         const int64_t grp = e / A.k_stride;
         const double *Kp = A.k_in_smem ? (sK + (grp - g0) * 4 * KC) : (A.K + grp * 4 * KC);
         if (A.chain == 1) {  // controller.reset() before every episode (tuning.py:879)
@@ -88,11 +98,16 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 
         double t = 0.0;
         int step = 0, env_on = 0, met_on = 0, violations = 0, term = QT_TERM_NONE;
-        double sum_err = 0.0, sum_err2 = 0.0, max_err = 0.0, sum_eff = 0.0, err_post = 0.0;
+        double err_post = 0.0;
+        cold[CR_SUM_ERR * T] = 0.0;
+        cold[CR_SUM_ERR2 * T] = 0.0;
+        cold[CR_SUM_EFF * T] = 0.0;
+        cold[CR_MAX_ERR * T] = 0.0;
+        cold[CR_OV_CUR * T] = 0.0;
+        cold[CR_OV_MAX * T] = 0.0;
         // overshoot detector state (utils/metrics.py:205-261), streamed
         bool prev_on = false, in_phase = false;
         int streak = 0, ov_count = 0;
-        double ov_cur = 0.0, ov_max = 0.0;
         int next_traj = 0, traj_slot = 0, next_data = 0, data_slot = 0;
 
         double tp[3], tv[3], ta[3];
@@ -108,27 +123,27 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             {
                 const bool on = err_pre <= P.crit_target_radius;
                 met_on += on ? 1 : 0;
-                sum_err += err_pre;
-                sum_err2 += err_pre * err_pre;
-                max_err = (step == 0 || err_pre > max_err) ? err_pre : max_err;
-                sum_eff += sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
+                cold[CR_SUM_ERR * T] += err_pre;
+                cold[CR_SUM_ERR2 * T] += err_pre * err_pre;
+                const double mx = cold[CR_MAX_ERR * T];
+                if (step == 0 || err_pre > mx) cold[CR_MAX_ERR * T] = err_pre;
+                cold[CR_SUM_EFF * T] += sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
                 if (step > 0) {
-                    const double over = err_pre - P.crit_target_radius;
                     if (prev_on && !on) {
                         in_phase = true;
                         streak = 1;
-                        ov_cur = over;
+                        cold[CR_OV_CUR * T] = err_pre - P.crit_target_radius;
                     } else if (in_phase && !on) {
                         streak += 1;
-                        ov_cur = fmax(ov_cur, over);
+                        cold[CR_OV_CUR * T] = fmax(cold[CR_OV_CUR * T], err_pre - P.crit_target_radius);
                     } else if (in_phase && on) {
                         if (streak >= P.overshoot_window) {
                             ov_count += 1;
-                            ov_max = fmax(ov_max, ov_cur);
+                            cold[CR_OV_MAX * T] = fmax(cold[CR_OV_MAX * T], cold[CR_OV_CUR * T]);
                         }
                         in_phase = false;
                         streak = 0;
-                        ov_cur = 0.0;
+                        cold[CR_OV_CUR * T] = 0.0;
                     }
                 }
                 prev_on = on;
@@ -176,11 +191,11 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             double actv[4];
             violations += validate_action(P, act, actv);
             if (euler)
-                integrate_euler(C, dt, s, actv);
+                integrate<true>(C, s, actv);
             else
-                integrate_rk4(C, dt, s, actv);
+                integrate<false>(C, s, actv);
             constrain_state(P, C, s);
-            t += dt;
+            t += C.dt;
             tg.template state<FULL>(P, t, tp, tv, ta);
             err_post = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
             term = termination_code(P, s, t);
@@ -197,9 +212,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             step += 1;
             err_pre = err_post;
         }
+        double ov_max = cold[CR_OV_MAX * T];
         if (in_phase && streak >= P.overshoot_window) {
             ov_count += 1;
-            ov_max = fmax(ov_max, ov_cur);
+            ov_max = fmax(ov_max, cold[CR_OV_CUR * T]);
         }
 
         const double n = (double)step;
@@ -210,10 +226,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         m[(int64_t)QT_M_FINAL_TIME * E] = t;
         m[(int64_t)QT_M_ENV_ON_TARGET * E] = (double)env_on;
         m[(int64_t)QT_M_MET_ON_TARGET * E] = (double)met_on;
-        m[(int64_t)QT_M_SUM_ERR * E] = sum_err;
-        m[(int64_t)QT_M_MAX_ERR * E] = max_err;
-        m[(int64_t)QT_M_SUM_ERR2 * E] = sum_err2;
-        m[(int64_t)QT_M_SUM_EFFORT * E] = sum_eff;
+        m[(int64_t)QT_M_SUM_ERR * E] = cold[CR_SUM_ERR * T];
+        m[(int64_t)QT_M_MAX_ERR * E] = cold[CR_MAX_ERR * T];
+        m[(int64_t)QT_M_SUM_ERR2 * E] = cold[CR_SUM_ERR2 * T];
+        m[(int64_t)QT_M_SUM_EFFORT * E] = cold[CR_SUM_EFF * T];
         m[(int64_t)QT_M_OVERSHOOT_COUNT * E] = (double)ov_count;
         m[(int64_t)QT_M_MAX_OVERSHOOT * E] = ov_max;
         m[(int64_t)QT_M_ENV_SUCCESS * E] =
@@ -242,7 +258,9 @@ template <int MOTION, bool LQI, bool FULL>
 static cudaError_t launch_one(const qt_params &P, const RolloutArgs &A, size_t smem, cudaStream_t st) {
     const int64_t blocks = (A.n_chains + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks <= 0) return cudaSuccess;
-    rollout_kernel<MOTION, LQI, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, A);
+    DynConsts C;
+    C.init(P);
+    rollout_kernel<MOTION, LQI, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, C, A);
     return cudaGetLastError();
 }
 
@@ -302,16 +320,18 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     A.data_slots = (int)data_slots;
 
     // K staging: with one episode per thread a block needs at most ceil(T / k_stride) + 1 groups
-    size_t smem = 0;
     A.k_in_smem = 0;
+    A.k_smem_doubles = 0;
     if (chain == 1) {
         int64_t groups = (kRolloutThreads + k_stride - 1) / k_stride + 1;
-        size_t bytes = (size_t)groups * 4 * k_cols * sizeof(double);
-        if (bytes <= 40 * 1024) {
+        size_t doubles = (size_t)groups * 4 * k_cols;
+        if (doubles * sizeof(double) <= 24 * 1024) {
             A.k_in_smem = 1;
-            smem = bytes;
+            A.k_smem_doubles = (int)doubles;
         }
     }
+    // staged gains + the per-thread cold-state tile (kColdRows x 128 doubles = 18 KB)
+    const size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
     const bool full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 ||
                       traj_out_dev != nullptr || feat_out_dev != nullptr;
 

@@ -13,7 +13,7 @@
 //  * sincos_shifted(): the stage angles of RK4 are the step's base angle plus a small increment
 //    (|delta| <= dt * max_angular_velocity = 0.1 rad by default).  sin/cos(a + delta) follow from
 //    sin/cos(a) by the angle-addition formulas with short Taylor polynomials for sin(delta) and
-//    cos(delta) - 1: 19 FP64 instructions, no integer work, no branches.  The increment is taken as
+//    cos(delta) - 1: 11-17 FP64 instructions, no integer work.  The increment is taken as
 //    fl(a + delta) - a, i.e. the function is evaluated at exactly the rounded stage angle the
 //    reference passes to np.sin / np.cos.
 //
@@ -57,7 +57,8 @@ QT_TRIG_CONST double c_trig[32] = {
     2.08767569878680989792e-09,
     0.0, 0.0, 0.0, 0.0, 0.0};
 
-constexpr double kShiftMax = 0.26;  // Taylor truncation error < 1e-17 up to here
+constexpr double kShiftMax = 0.26;        // full Taylor polynomials: truncation error < 1e-17 up to here
+constexpr double kShiftSmall = 0.0078125;  // 2^-7: sin through d^5, cos through d^6 suffice (< 4e-19)
 
 // Out-of-line so the (practically never taken) huge-argument path costs the hot loop one
 // predicated call instead of an inlined Payne-Hanek reduction.
@@ -105,25 +106,32 @@ QT_TRIG_FN void sincos_pi(double x, double &s, double &c) {
     c = ((k + 1) & 2) ? -b : b;
 }
 
-// sin/cos of `arg`, given sin/cos of `base`, where arg = fl(base + small increment).
-// The caller guarantees |arg - base| <= kShiftMax.
-QT_TRIG_FN void sincos_shifted(double base, double sb, double cb, double arg, double &s,
-                                               double &c) {
+// sin/cos of `arg`, given sin/cos of `base`, where arg = fl(base + small increment) and the
+// caller guarantees |arg - base| <= kShiftMax (SMALL = false) or <= kShiftSmall (SMALL = true:
+// two Taylor terms fewer per polynomial, truncation error < 4e-19).
+template <bool SMALL>
+QT_TRIG_FN void sincos_shifted(double base, double sb, double cb, double arg, double &s, double &c) {
     const double d = arg - base;  // exact (Sterbenz) or the increment itself when base is tiny
     const double z = d * d;
-    double p = fma(z, c_trig[20], c_trig[19]);
-    double q = fma(z, c_trig[26], c_trig[25]);
-    p = fma(z, p, c_trig[18]);
-    q = fma(z, q, c_trig[24]);
-    p = fma(z, p, c_trig[17]);
-    q = fma(z, q, c_trig[23]);
-    p = fma(z, p, c_trig[16]);
-    q = fma(z, q, c_trig[22]);
+    double p, q;
+    if (SMALL) {
+        p = fma(z, c_trig[17], c_trig[16]);
+        q = fma(z, c_trig[23], c_trig[22]);
+    } else {
+        p = fma(z, c_trig[20], c_trig[19]);
+        q = fma(z, c_trig[26], c_trig[25]);
+        p = fma(z, p, c_trig[18]);
+        q = fma(z, q, c_trig[24]);
+        p = fma(z, p, c_trig[17]);
+        q = fma(z, q, c_trig[23]);
+        p = fma(z, p, c_trig[16]);
+        q = fma(z, q, c_trig[22]);
+    }
     q = fma(z, q, c_trig[21]);
     const double sd = fma(d * z, p, d);  // sin(d)
     const double cm = z * q;             // cos(d) - 1
-    s = sb + fma(cb, sd, sb * cm);
-    c = cb + fma(-sb, sd, cb * cm);
+    s = fma(cb, sd, fma(sb, cm, sb));    // sin(b) cos(d) + cos(b) sin(d)
+    c = fma(-sb, sd, fma(cb, cm, cb));   // cos(b) cos(d) - sin(b) sin(d)
 }
 
 }  // namespace qt
