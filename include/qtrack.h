@@ -178,7 +178,7 @@ int qt_observe_batched(qt_context *ctx, const qt_params *params, int64_t E,
 
 /* ---- A10: RiccatiLQRController.compute_action ---------------------------------------------
  * riccati_lqr.py:779-967 for a batch of observations.  K is row-major [groups][4][k_cols],
- * k_cols = 6 (LQR) or 9 (LQI: K_pd | K_i); episode e uses group e / k_stride.
+ * 16-byte aligned, k_cols = 6 (LQR) or 9 (LQI: K_pd | K_i); episode e uses group e / k_stride.
  * integral_io [3][E] and saturation_io [E] hold the controller state (NULL when !use_lqi /
  * not wanted).  action_out [4][E].                                                          */
 int qt_compute_action_batched(qt_context *ctx, const qt_params *params, int64_t E,

@@ -364,6 +364,7 @@ extern "C" int qt_compute_action_batched(qt_context *ctx, const qt_params *param
     QT_REQUIRE(ctx, params && obs_dev && K_dev && action_out_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0, "E < 0");
     QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
     if (E == 0) return QT_OK;
     if (k_stride < 1) k_stride = 1;
     CtrlArgs A{E, k_stride, obs_dev, K_dev, integral_io_dev, saturation_io_dev, action_out_dev};
@@ -386,8 +387,10 @@ extern "C" int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t
     QT_REQUIRE(ctx, params && state_io_dev && time_io_dev && tparams_dev && counters_io_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0, "E < 0");
     QT_REQUIRE(ctx, action_in_dev || K_dev, "either an action or a gain matrix is required");
-    if (!action_in_dev)
+    if (!action_in_dev) {
         QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+        QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
+    }
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
     if (E == 0) return QT_OK;
     if (k_stride < 1) k_stride = 1;

@@ -28,6 +28,7 @@ struct RolloutArgs {
     int max_steps;
     int k_in_smem;
     int k_smem_doubles;  // doubles reserved for the staged gains at the start of shared memory
+    int env_bounds_check;  // 0 when the controller's clamps lie inside the env's action limits
     const double *state0, *tparams, *K;
     double *metrics, *ctrl_state, *final_state, *traj;
     float *feat, *actf;
@@ -113,6 +114,11 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         double tp[3], tv[3], ta[3];
         tg.template state<FULL>(P, t, tp, tv, ta);
         double err_pre = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
+        Trig B;  // sin/cos of the current attitude, carried from step to step (trig_rebase)
+        {
+            const double e0[3] = {s[6], s[7], s[8]};
+            trig_full(e0, B);
+        }
 
         while (term == QT_TERM_NONE && step < A.max_steps) {
             // ---- controller on the pre-step observation
@@ -188,13 +194,14 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             }
 
             // ---- env.step (quadcopter_env.py:171-207)
-            double actv[4];
-            violations += validate_action(P, act, actv);
+            double actv[4], eta_old[3];
+            violations += A.env_bounds_check ? validate_action<true>(P, act, actv) : validate_action<false>(P, act, actv);
             if (euler)
-                integrate<true>(C, s, actv);
+                integrate<true>(C, s, actv, B, eta_old);
             else
-                integrate<false>(C, s, actv);
+                integrate<false>(C, s, actv, B, eta_old);
             constrain_state(P, C, s);
+            trig_rebase(eta_old, s, (step & 15) == 15, B);
             t += C.dt;
             tg.template state<FULL>(P, t, tp, tv, ta);
             err_post = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
@@ -289,6 +296,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0 && max_steps >= 0 && max_steps < (1ll << 31), "bad E / max_steps");
     QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
     QT_REQUIRE(ctx, (feat_out_dev == nullptr) == (act_out_dev == nullptr), "feat/act must come together");
     if (E == 0) return QT_OK;
@@ -320,11 +328,14 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     A.data_slots = (int)data_slots;
 
     // K staging: with one episode per thread a block needs at most ceil(T / k_stride) + 1 groups
+    // the env's range checks can only trigger if the controller is allowed to exceed the env's limits
+    A.env_bounds_check = !(params->ctrl_min_thrust >= params->min_thrust && params->ctrl_max_thrust <= params->max_thrust &&
+                           params->ctrl_max_rate <= params->max_angular_rate && params->ctrl_max_rate >= 0.0);
     A.k_in_smem = 0;
     A.k_smem_doubles = 0;
     if (chain == 1) {
         int64_t groups = (kRolloutThreads + k_stride - 1) / k_stride + 1;
-        size_t doubles = (size_t)groups * 4 * k_cols;
+        size_t doubles = ((size_t)groups * 4 * k_cols + 1) & ~(size_t)1;  // keep the cold tile 16-byte aligned
         if (doubles * sizeof(double) <= 24 * 1024) {
             A.k_in_smem = 1;
             A.k_smem_doubles = (int)doubles;
