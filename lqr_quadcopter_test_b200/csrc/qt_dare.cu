@@ -39,7 +39,11 @@ template <int N>
 struct Lay {
     static constexpr int LD = (N + 1) & ~1;        // even row stride: rows stay 16-byte aligned
     static constexpr int MAT = N * LD;
-    static constexpr int TEAM = 6 * MAT + 4 * LD;  // sA sG sH sX sY sS | pivot row (3 LD) | column (LD)
+    static constexpr int RAW = 6 * MAT + 4 * LD;   // sA sG sH sX sY sS | pivot row (3 LD) | column (LD)
+    // Teams of one warp issue the same 16-byte broadcast load at the same offset inside their own
+    // block; padding the block to 2 (mod 16) doubles = 4 (mod 32) banks puts up to 8 teams on
+    // disjoint bank groups (the unpadded N = 6 layout was a 5-way conflict: ncu, profiles/r01_a).
+    static constexpr int TEAM = RAW + ((2 - RAW % 16) + 16) % 16;
     static constexpr int TEAMS = 32 / N;           // systems per warp
     static constexpr int SLOTS = TEAMS + ((32 % N) ? 1 : 0);  // + a ghost team for leftover lanes
 };
@@ -94,36 +98,60 @@ __device__ __forceinline__ void store_row(double *__restrict__ M, int row, const
     }
 }
 
+// c1[j] = sum_k x1[k] * Y[k][j] and c2[j] = sum_k x2[k] * Y[k][j]: two products sharing the loads of Y
+template <int N>
+__device__ __forceinline__ void row_times2(const double (&x1)[N], const double (&x2)[N],
+                                           const double *__restrict__ Y, double (&c1)[N], double (&c2)[N]) {
+    constexpr int LD = Lay<N>::LD;
+#pragma unroll
+    for (int j = 0; j < N; j++) c1[j] = c2[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            const double2 y = *reinterpret_cast<const double2 *>(Y + k * LD + j);
+            c1[j] = fma(x1[k], y.x, c1[j]);
+            c2[j] = fma(x2[k], y.x, c2[j]);
+            if (j + 1 < N) {
+                c1[j + 1] = fma(x1[k], y.y, c1[j + 1]);
+                c2[j + 1] = fma(x2[k], y.y, c2[j + 1]);
+            }
+        }
+    }
+}
+
 // Gauss-Jordan with partial pivoting, one matrix row per lane.  On exit the lane that served
 // as pivot for column c holds row c of W^-1 [R1 | R2] in (r1 | r2); it writes them to
 // X[c][:] / Y[c][:].  Returns false if a pivot was zero / not finite.
+//
+// Per column: (1) pivot search without shared memory — every lane publishes a 32-bit key (the
+// high word of |w[c]| with the lane index in its low 5 bits, 0 for rows already used) and reads
+// its team mates' keys with shuffles; the top 27 bits of the magnitude are plenty for partial
+// pivoting; (2) the pivot lane writes its row and 1/pivot to shared memory; (3) the other lanes
+// eliminate.  Rows are not normalised until the end.  The multiplier is w[c] * (1/pivot): the
+// matrices of the reference's designs are sparse, and CUDA's double division takes its slow path
+// for a zero numerator, which made one third of the first version's instructions.
 template <int N, bool TWO>
 __device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], double (&r2)[N],
-                                             double *__restrict__ sRow, double *__restrict__ sCol,
-                                             double *__restrict__ X, double *__restrict__ Y, int li) {
+                                             double *__restrict__ sRow, double *__restrict__ X,
+                                             double *__restrict__ Y, int li, int team_base) {
     constexpr int LD = Lay<N>::LD;
     bool used = false, ok = true;
     int my_col = 0;
-    double my_piv = 1.0;
+    double my_inv = 1.0;
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        sCol[li] = used ? -1.0 : fabs(w[c]);
-        __syncwarp();
-        int p = 0;
-        double best = sCol[0];
+        const unsigned hi = (unsigned)__double2hiint(w[c]) & 0x7fffffffu;
+        const unsigned key = used ? 0u : ((hi & 0xffffffe0u) | (unsigned)(31 - li));
+        unsigned best = 0u;
 #pragma unroll
-        for (int k = 1; k < N; k++) {
-            const double v = sCol[k];
-            if (v > best) {
-                best = v;
-                p = k;
-            }
-        }
-        if (!(best > 0.0) || !(best < 1.0e300)) ok = false;
+        for (int k = 0; k < N; k++) best = max(best, __shfl_sync(0xffffffffu, key, team_base + k));
+        const int p = 31 - (int)(best & 31u);
+        if ((best >> 5) == 0u || best >= 0x7ff00000u) ok = false;  // zero / NaN / inf pivot
         if (li == p) {
             used = true;
             my_col = c;
-            my_piv = w[c];
+            my_inv = 1.0 / w[c];
             // only columns > c of W are still needed by the other rows
 #pragma unroll
             for (int j = c & ~1; j < N; j += 2) {
@@ -134,12 +162,17 @@ __device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], do
             }
             store_row<N>(sRow + LD, 0, r1);
             if (TWO) store_row<N>(sRow + 2 * LD, 0, r2);
+            sRow[3 * LD] = my_inv;
         }
         __syncwarp();
         if (li != p) {
-            const double f = w[c] / sRow[c];
+            const double f = w[c] * sRow[3 * LD];
 #pragma unroll
-            for (int j = c + 1; j < N; j++) w[j] = fma(-f, sRow[j], w[j]);
+            for (int j = (c + 1) & ~1; j < N; j += 2) {
+                const double2 y = *reinterpret_cast<const double2 *>(sRow + j);
+                if (j > c) w[j] = fma(-f, y.x, w[j]);
+                if (j + 1 < N) w[j + 1] = fma(-f, y.y, w[j + 1]);
+            }
             w[c] = 0.0;
 #pragma unroll
             for (int j = 0; j < N; j += 2) {
@@ -158,11 +191,10 @@ __device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], do
         }
         __syncwarp();
     }
-    const double inv = 1.0 / my_piv;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        r1[j] *= inv;
-        if (TWO) r2[j] *= inv;
+        r1[j] *= my_inv;
+        if (TWO) r2[j] *= my_inv;
     }
     store_row<N>(X, my_col, r1);
     if (TWO) store_row<N>(Y, my_col, r2);
@@ -170,13 +202,16 @@ __device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], do
     return ok;
 }
 
+// (launch bounds: resident blocks per SM the register allocator must allow — the kernel is
+// latency-bound, so occupancy matters: 4 blocks for N <= 6, 3 for N = 9)
 template <int N>
-__global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_constant__ DareArgs D) {
+__global__ void __launch_bounds__(kDareWarps * 32, (N <= 6 ? 4 : (N <= 9 ? 3 : 1)))
+    dare_kernel(const __grid_constant__ DareArgs D) {
     extern __shared__ __align__(16) double smem[];
     using L = Lay<N>;
     constexpr int LD = L::LD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int team = lane / N, li = lane % N;
+    const int team = lane / N, li = lane % N, team_base = lane - li;
     const int64_t sys = ((int64_t)blockIdx.x * kDareWarps + warp) * L::TEAMS + team;
     const int n = D.n, m = D.m;
     bool ghost = (team >= L::TEAMS) || (sys >= D.batch);
@@ -184,8 +219,7 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
 
     double *tb = smem + (size_t)(warp * L::SLOTS + team) * L::TEAM;
     double *sA = tb, *sG = tb + L::MAT, *sH = tb + 2 * L::MAT, *sX = tb + 3 * L::MAT,
-           *sY = tb + 4 * L::MAT, *sS = tb + 5 * L::MAT, *sRow = tb + 6 * L::MAT,
-           *sCol = tb + 6 * L::MAT + 3 * LD;
+           *sY = tb + 4 * L::MAT, *sS = tb + 5 * L::MAT, *sRow = tb + 6 * L::MAT;  // sRow: 3 LD + 1/pivot
 
     const double *Ap = ghost ? nullptr : D.A + sys * D.sA;
     const double *Bp = ghost ? nullptr : D.B + sys * D.sB;
@@ -207,7 +241,7 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
             r1[j] = (!ghost && li < m && j < n) ? Bp[j * m + li] : 0.0;
             r2[j] = 0.0;
         }
-        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sCol, sX, sY, li);
+        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sX, sY, li, team_base);
         row_times<N, false>(brow, sX, g);  // G0 = B Z
     }
 
@@ -229,9 +263,10 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
                 r1[j] = a[j];
                 r2[j] = g[j];
             }
-            ok &= gauss_jordan<N, true>(w, r1, r2, sRow, sCol, sX, sY, li);  // X = W^-1 A, Y = W^-1 G
+            ok &= gauss_jordan<N, true>(w, r1, r2, sRow, sX, sY, li, team_base);  // X = W^-1 A, Y = W^-1 G
         }
-        row_times<N, false>(a, sX, an);  // A X
+        double hx[N];
+        row_times2<N>(a, h, sX, an, hx);  // A X and H X share the loads of X
         {
             double t[N];
             row_times<N, false>(a, sY, t);  // A Y
@@ -240,9 +275,7 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
             row_times_T<N>(t, sA, gn);  // G + (A Y) A'
         }
         {
-            double s[N];
-            row_times<N, false>(h, sX, s);  // H X
-            store_row<N>(sS, li, s);
+            store_row<N>(sS, li, hx);
             __syncwarp();
             // H + A' (H X): row i needs column i of A
             double acol[N];
@@ -252,7 +285,7 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
             for (int j = 0; j < N; j++) hn[j] = h[j];
             row_times<N, true>(acol, sS, hn);
         }
-        // convergence: ||H+ - H||_F <= tol ||H+||_F, reduced over the team through sCol
+        // convergence: ||H+ - H||_F <= tol ||H+||_F, reduced over the team through sRow
         double d2 = 0.0, h2 = 0.0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -322,7 +355,7 @@ __global__ void __launch_bounds__(kDareWarps * 32) dare_kernel(const __grid_cons
         row_times<N, true>(bcol, sX, w);    // R + B'(PB)
         row_times<N, false>(bcol, sY, r1);  // B'(PA)
         __syncwarp();
-        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sCol, sG, sH, li);  // K rows -> sG
+        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sG, sH, li, team_base);  // K rows -> sG
         if (!ghost && D.K && li < m) {
 #pragma unroll
             for (int j = 0; j < N; j++)
