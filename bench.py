@@ -241,7 +241,8 @@ def run_gpu_arm(args) -> None:
     gpu_launches = ctx.launches - launches0
     clock_info = clocks.summary()
     kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
-    total_steps_rank = float(metrics[0].sum().item()) * args.steps
+    steps_per_pass = float(sums.cpu()[13])  # S_SUM_STEPS of qt_reduce_summary: env steps of the last pass
+    total_steps_rank = steps_per_pass * args.steps
     el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([total_steps_rank], dtype=torch.float64, device=dev)
     if world > 1:
@@ -276,7 +277,7 @@ def run_gpu_arm(args) -> None:
     # ---- rank 0 only: roofline denominators, DARE throughput, CPU baseline --------------------------
     fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
     k_ms = statistics.mean(kernel_ms)
-    steps_per_launch = float(metrics[0].sum().item())
+    steps_per_launch = steps_per_pass
     achieved = steps_per_launch * FLOPS_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
     peaks = {}
     try:
@@ -285,9 +286,15 @@ def run_gpu_arm(args) -> None:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     algo_bytes = (24 + 16) * 8.0 * E
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        tr = json.load(open(ROOT / "profiles" / "ncu_traffic.json"))["rollout_kernel_linear_lqr_2^20x3000"]
+        traffic = tr["dram_bytes_per_launch"] if E == EPISODES_PER_GPU else None
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "fp64", "kernel": "rollout_kernel<linear, LQR, lean>", "achieved": achieved, "peak": fp64_tflops,
-        "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops > 0 else None, "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops > 0 else None, "traffic": traffic,
         "peak_source": "register-resident DFMA probe (qt_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
         "algorithmic_flops_per_env_step": FLOPS_PER_ENV_STEP, "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms * args.steps / elapsed_ms if world == 1 else None,

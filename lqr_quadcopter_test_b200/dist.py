@@ -34,7 +34,8 @@ def init_process_group(backend: str | None = None) -> tuple[int, int, int]:
         if backend == "nccl":
             torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rank, world_size=size)
+        kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=size, **kw)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, size, local
