@@ -79,4 +79,35 @@ rows = r[0].shape[0]
 out["config5_teacher_dataset"] = {"episodes": E5, "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3,
                                   "write_gbs": rows * 88 / ms * 1e3 / 1e9, "env_steps_per_s": E5 * 3000 / ms * 1e3}
 print("config5_teacher_dataset", out["config5_teacher_dataset"], flush=True)
+# HBM-bound variant: log EVERY step of every episode (24 fp64 fields = 192 B per env step), the layout
+# Evaluator.run_episode consumes.  65 536 episodes x 3000 steps x 192 B = 37.7 GB of writes.
+E6 = int(65536 * args.scale)
+seeds6 = torch.arange(E6, dtype=torch.int64, device=dev) + 42
+env = EnvConfig()
+env.target.motion_type = "linear"
+ctrl = RiccatiLQRController(config={})
+peaks = json.load(open(pathlib.Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json")) if (
+    pathlib.Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
+import numpy as _np
+from lqr_quadcopter_test_b200 import params as P
+prm = ctrl.kernel_params(env, SuccessCriteria())
+f64 = dict(dtype=torch.float64, device=dev)
+s0, tp6 = torch.empty((12, E6), **f64), torch.empty((12, E6), **f64)
+ctx.reset_batched(prm, seeds6, s0, tp6)
+K6 = torch.as_tensor(_np.ascontiguousarray(ctrl.K), **f64)
+met6 = torch.empty((16, E6), **f64)
+for stride in (1, 2, 4):
+    slots = (3000 + stride - 1) // stride
+    log = torch.empty((slots, P.TRAJ_FIELDS, E6), **f64)  # preallocated: the kernel alone is timed
+    ms, _ = timed(lambda: ctx.rollout(prm, E6, 3000, 1, s0, tp6, K6, 6, E6, met6, None, None, log, stride, slots), reps=2)
+    steps = float(met6[0].sum().item())
+    gbs = steps / stride * 192 / ms * 1e3 / 1e9
+    out[f"trajectory_log_stride{stride}"] = {"episodes": E6, "ms": ms, "env_steps_per_s": steps / ms * 1e3,
+                                             "log_write_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
+                                             "hbm_frac": gbs / peaks["hbm_gbs"],
+                                             "note": "kernel only, log preallocated; 192 B (24 fp64 fields) per logged step; "
+                                                     "the peak is a copy (read+write) figure, this is write-only traffic"}
+    print(f"trajectory_log_stride{stride}", out[f"trajectory_log_stride{stride}"], flush=True)
+    del log
+    torch.cuda.empty_cache()
 print(json.dumps(out))
