@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QT_ABI_VERSION 1
+#define QT_ABI_VERSION 2
 
 #define QT_STATE_DIM 12     /* env/quadcopter_env.py:63-70  [p(3) v(3) roll,pitch,yaw  p,q,r] */
 #define QT_ACTION_DIM 4     /* thrust, roll_rate, pitch_rate, yaw_rate (controllers/base.py:28) */
@@ -52,6 +52,14 @@ enum qt_motion {
 };
 
 enum qt_integrator { QT_INTEGRATOR_RK4 = 0, QT_INTEGRATOR_EULER = 1 }; /* quadcopter_env.py:309-312 */
+
+/* Control law evaluated inside the kernels.
+ *   QT_CTRL_RICCATI  u = K e (+ K_i I)          controllers/riccati_lqr.py:779-967 (also the heuristic
+ *                    LQRController, controllers/__init__.py:576-686: same law, closed-form K)
+ *                    gains: K row-major [4][6] (use_lqi = 0) or [4][9] (use_lqi = 1)
+ *   QT_CTRL_PID      per-axis P/I/D on the position error, controllers/__init__.py:243-379
+ *                    gains: row-major [4][3] = kp | ki | kd | (unused row)                         */
+enum qt_controller { QT_CTRL_RICCATI = 0, QT_CTRL_PID = 1 };
 
 /* quadcopter_env.py:513-535; 0 = the step cap ended the loop, not the environment */
 enum qt_termination {
@@ -123,13 +131,14 @@ typedef struct qt_params {
     double ctrl_dt, ctrl_hover_thrust, ctrl_max_thrust, ctrl_min_thrust, ctrl_max_rate;
     double integral_limit, integral_zero_threshold;
     double ff_velocity_gain[3], ff_acceleration_gain[3];
-    double ff_max_velocity, ff_max_acceleration;
+    double ff_max_velocity, ff_max_acceleration;   /* integral_limit is shared with the PID law (:212) */
     int32_t motion_type;          /* enum qt_motion, one per launch                         */
     int32_t integrator;           /* enum qt_integrator                                     */
     int32_t use_lqi;              /* riccati_lqr.py:474                                     */
     int32_t feedforward_enabled;  /* riccati_lqr.py:494                                     */
     int32_t overshoot_window;     /* metrics.py:208, default 10                             */
-    int32_t reserved0, reserved1, reserved2;
+    int32_t controller_type;      /* enum qt_controller                                     */
+    int32_t reserved1, reserved2;
 } qt_params;
 
 typedef struct qt_context qt_context;
@@ -180,7 +189,9 @@ int qt_observe_batched(qt_context *ctx, const qt_params *params, int64_t E,
  * riccati_lqr.py:779-967 for a batch of observations.  K is row-major [groups][4][k_cols],
  * 16-byte aligned, k_cols = 6 (LQR) or 9 (LQI: K_pd | K_i); episode e uses group e / k_stride.
  * integral_io [3][E] and saturation_io [E] hold the controller state (NULL when !use_lqi /
- * not wanted).  action_out [4][E].                                                          */
+ * not wanted).  For QT_CTRL_PID, K is [groups][4][3] (k_cols = 3) and integral_io is [4][E]:
+ * rows 0-2 the integral error, row 3 the time of the previous call (NaN = none yet, i.e.
+ * PIDController._last_time is None).  action_out [4][E].                                     */
 int qt_compute_action_batched(qt_context *ctx, const qt_params *params, int64_t E,
                               const double *obs_dev, const double *K_dev, int32_t k_cols,
                               int64_t k_stride, double *integral_io_dev,
@@ -208,7 +219,8 @@ int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t E, double 
  * never resets the controller between episodes, eval.py:198-213).
  *   state0 [12][E], tparams [12][E], K [groups][4][k_cols], metrics_out [16][E],
  *   ctrl_state_io [4][n_chains] or NULL (n_chains = ceil(E / chain)): LQI integrator (3 rows)
- *   and saturation count of each chain's controller; read as the initial controller state
+ *   and saturation count of each chain's controller (PID: integral error and, in row 3, the
+ *   time of the previous call, NaN = none); read as the initial controller state
  *   when chain > 1 (Evaluator semantics: whatever state the controller object carries),
  *   ignored on entry when chain == 1 (reset per episode); always written back on exit,
  *   final_state_out [12][E] or NULL,

@@ -9,7 +9,7 @@ include/qtrack.h); this package is the thin host layer.  There is no CPU fallbac
 """
 from .config import (EnvConfig, LoggingParams, QuadcopterParams, SimulationParams, TargetParams)
 from .config import SuccessCriteria as EnvSuccessCriteria
-from .controller import (ACTION_KEYS, BaseController, LQRController, RiccatiLQRController,
+from .controller import (ACTION_KEYS, BaseController, LQRController, PIDController, RiccatiLQRController,
                          build_augmented_lqi_system, build_linearized_system, heuristic_lqr_gain,
                          solve_dare, solve_dare_batched)
 from .env import BatchedQuadcopterEnv, QuadcopterEnv
@@ -23,7 +23,7 @@ __version__ = "0.1.0"
 __all__ = [
     "EnvConfig", "QuadcopterParams", "SimulationParams", "TargetParams", "LoggingParams",
     "EnvSuccessCriteria", "SuccessCriteria", "QuadcopterEnv", "BatchedQuadcopterEnv",
-    "RiccatiLQRController", "LQRController", "BaseController", "ACTION_KEYS", "solve_dare",
+    "RiccatiLQRController", "LQRController", "PIDController", "BaseController", "ACTION_KEYS", "solve_dare",
     "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
     "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
     "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",

@@ -247,10 +247,28 @@ class _GainController(BaseController):
     def effective_use_lqi(self) -> bool:
         return False
 
+    def k_cols(self) -> int:
+        """Doubles per row of the 4-row gain record the kernels read (6 LQR, 9 LQI, 3 PID)."""
+        return 9 if self.effective_use_lqi() else 6
+
+    def carries_state(self) -> bool:
+        """True if state inside the controller object influences its next action."""
+        return self.effective_use_lqi()
+
     def kernel_params(self, env_config=None, criteria=None) -> QtParams:
         p = make_params(env_config, self, criteria)
         p.use_lqi = 1 if self.effective_use_lqi() else 0
         return p
+
+    # controller state as the kernels see it: [integral(3), saturation count | PID last time]
+    def state_vector(self) -> np.ndarray:
+        integ = getattr(self, "integral_state", None)
+        return np.array([*(integ if integ is not None else np.zeros(3)), float(self._saturation_count)])
+
+    def load_state_vector(self, v: np.ndarray, absolute_count: bool) -> None:
+        if getattr(self, "integral_state", None) is not None:
+            self.integral_state = np.array(v[0:3], dtype=np.float64)
+        self._saturation_count = int(v[3]) if absolute_count else self._saturation_count + int(v[3])
 
     # -- scalar interface --------------------------------------------------------------------
     def _device_state(self):
@@ -262,7 +280,7 @@ class _GainController(BaseController):
             self._dev = {
                 "ctx": ctx,
                 "obs": torch.zeros((22, 1), dtype=torch.float64, device=dev),
-                "integral": torch.zeros((3, 1), dtype=torch.float64, device=dev),
+                "integral": torch.zeros((4, 1), dtype=torch.float64, device=dev),
                 "sat": torch.zeros(1, dtype=torch.int64, device=dev),
                 "action": torch.zeros((4, 1), dtype=torch.float64, device=dev),
                 "K": torch.as_tensor(np.ascontiguousarray(self.effective_gain()), dtype=torch.float64, device=dev),
@@ -280,15 +298,15 @@ class _GainController(BaseController):
         ctx = d["ctx"]
         ctx.bind_torch_stream()
         d["obs"].copy_(torch.from_numpy(obs_vec.reshape(22, 1)))
-        lqi = self.effective_use_lqi()
-        if lqi:
-            d["integral"].copy_(torch.from_numpy(np.asarray(integral, dtype=np.float64).reshape(3, 1)))
+        stateful = integral is not None
+        if stateful:
+            n = len(integral)
+            d["integral"][:n].copy_(torch.from_numpy(np.asarray(integral, dtype=np.float64).reshape(n, 1)))
         d["sat"].zero_()
-        k_cols = 9 if lqi else 6
-        ctx.compute_action_batched(d["params"], 1, d["obs"], d["K"], k_cols, 1,
-                                   d["integral"] if lqi else None, d["sat"], d["action"])
+        ctx.compute_action_batched(d["params"], 1, d["obs"], d["K"], self.k_cols(), 1,
+                                   d["integral"] if stateful else None, d["sat"], d["action"])
         action = d["action"].cpu().numpy().reshape(4)
-        new_integral = d["integral"].cpu().numpy().reshape(3) if lqi else None
+        new_integral = d["integral"].cpu().numpy().reshape(4)[: len(integral)] if stateful else None
         saturated = bool(int(d["sat"].cpu()[0]))
         return action, new_integral, saturated
 
@@ -299,14 +317,15 @@ class _GainController(BaseController):
 
         ctx = _lib.get_context()
         E = int(obs.shape[1])
-        lqi = self.effective_use_lqi()
+        stateful = self.carries_state()
         Kt = K if K is not None else torch.as_tensor(
             np.ascontiguousarray(self.effective_gain()), dtype=torch.float64, device=obs.device)
         action = torch.empty((4, E), dtype=torch.float64, device=obs.device)
-        if lqi and integral is None:
-            integral = torch.zeros((3, E), dtype=torch.float64, device=obs.device)
-        ctx.compute_action_batched(self.kernel_params(), E, obs.contiguous(), Kt, 9 if lqi else 6,
-                                   k_stride or E, integral if lqi else None, saturation, action)
+        if stateful and integral is None:
+            integral = torch.zeros((4, E), dtype=torch.float64, device=obs.device)
+            integral[3] = float("nan")
+        ctx.compute_action_batched(self.kernel_params(), E, obs.contiguous(), Kt, self.k_cols(),
+                                   k_stride or E, integral if stateful else None, saturation, action)
         return action
 
     def get_control_components(self) -> dict | None:
@@ -351,6 +370,64 @@ class LQRController(_GainController):
         return dict(zip(ACTION_KEYS, (float(a) for a in action)))
 
     def reset(self) -> None:
+        self.last_control_components = None
+
+
+class PIDController(_GainController):
+    """PID position controller (controllers/__init__.py:116-395): per-axis P/I/D on the position
+    error mapped to thrust / pitch rate / -roll rate, optional feedforward.  The gain record the
+    kernels read is ``[kp | ki | kd | 0]`` (4 x 3).  State: ``integral_error`` and the time of the
+    previous call (the reference derives dt from observation["time"])."""
+
+    def __init__(self, config: dict | None = None):
+        config = config or {}
+        super().__init__(name="pid", config=config, mass=config.get("mass", 1.0),
+                         gravity=config.get("gravity", 9.81))
+        self.dt = config.get("dt", 0.01)
+        self.use_lqi = False
+        self.integral_zero_threshold = 0.01
+        self._init_limits_and_ff(config)
+        self.kp_pos = self._vec(config.get("kp_pos", config.get("kp", [0.01, 0.01, 4.0])))
+        self.ki_pos = self._vec(config.get("ki_pos", config.get("ki", [0.0, 0.0, 0.0])))
+        self.kd_pos = self._vec(config.get("kd_pos", config.get("kd", [0.06, 0.06, 2.0])))
+        self.integral_limit = config.get("integral_limit", 0.0)
+        self.integral_error = np.zeros(3)
+        self._last_time: float | None = None
+
+    @staticmethod
+    def _vec(value) -> np.ndarray:
+        return np.array(value, dtype=np.float64) if hasattr(value, "__len__") else np.array([value] * 3, dtype=np.float64)
+
+    def effective_gain(self) -> np.ndarray:
+        return np.stack([self.kp_pos, self.ki_pos, self.kd_pos, np.zeros(3)])
+
+    def k_cols(self) -> int:
+        return 3
+
+    def carries_state(self) -> bool:
+        # integral_limit == 0 (the default) clips the integral to zero after every update, and a
+        # stale _last_time only makes the first dt of the next episode negative instead of zero -
+        # both skip the update - so such a controller behaves identically with or without reset().
+        return self.integral_limit != 0
+
+    def state_vector(self) -> np.ndarray:
+        return np.array([*self.integral_error, float("nan") if self._last_time is None else float(self._last_time)])
+
+    def load_state_vector(self, v: np.ndarray, absolute_count: bool) -> None:
+        self.integral_error = np.array(v[0:3], dtype=np.float64)
+        self._last_time = None if np.isnan(v[3]) else float(v[3])
+
+    def compute_action(self, observation: dict) -> dict:
+        _validate_observation(observation)
+        obs_vec = observation_to_vector(observation)
+        action, state, _ = self._launch_scalar(obs_vec, self.state_vector())
+        self.load_state_vector(state, True)
+        self.last_control_components = {"integral_error": self.integral_error.copy()}
+        return dict(zip(ACTION_KEYS, (float(a) for a in action)))
+
+    def reset(self) -> None:
+        self.integral_error = np.zeros(3)
+        self._last_time = None
         self.last_control_components = None
 
 

@@ -53,6 +53,7 @@ extern "C" void qt_params_default(qt_params *p) {
     p->use_lqi = 0;
     p->feedforward_enabled = 0;
     p->overshoot_window = 10;
+    p->controller_type = QT_CTRL_RICCATI;
 }
 
 extern "C" int qt_create(int device, qt_context **out) {
@@ -130,7 +131,7 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     if (!ctx) return QT_ERR_ARG;
     QT_REQUIRE(ctx, params && seeds_host && K_host && metrics_host, "null pointer");
     QT_REQUIRE(ctx, E >= 0, "E < 0");
-    QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, k_cols == (params->controller_type == QT_CTRL_PID ? 3 : (params->use_lqi ? 9 : 6)), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
     if (E == 0) return QT_OK;
     DeviceGuard guard(ctx->device);
     // scratch layout: seeds | state0 [12][E] | tparams [12][E] | metrics [16][E] | K

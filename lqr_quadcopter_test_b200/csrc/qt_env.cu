@@ -171,13 +171,44 @@ struct CtrlArgs {
     double *action;
 };
 
-template <bool LQI>
+// Controller state layout for the stand-alone calls: integral [3][E] (LQI) or [4][E] (PID: row 3 is
+// the time of the previous call, NaN = none).
+template <int CTRL>
+__device__ __forceinline__ void run_controller(const qt_params &P, const double *K, int64_t E, int64_t e,
+                                               const double (&s)[12], const double (&tp)[3], const double (&tv)[3],
+                                               const double (&ta)[3], double t, double *integral,
+                                               int64_t *saturation, double (&act)[4]) {
+    constexpr int KC = CtrlCols<CTRL>::value;
+    double integ[3] = {0.0, 0.0, 0.0};
+    const bool stateful = (CTRL != CK_LQR) && integral;
+    if (stateful) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) integ[i] = integral[(int64_t)i * E + e];
+    }
+    if constexpr (CTRL == CK_PID) {
+        double last_time = stateful ? integral[(int64_t)3 * E + e] : __longlong_as_double(0x7ff8000000000000LL);
+        pid_action<true>(P, K, s, tp, tv, ta, t, integ, last_time, act);
+        if (stateful) integral[(int64_t)3 * E + e] = last_time;
+    } else {
+        const double err = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
+        int sat = 0;
+        ctrl_action<CTRL == CK_LQI, true>(P, K, s, tp, tv, ta, err, integ, sat, act);
+        if (saturation) saturation[e] += sat;
+    }
+    if (stateful) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) integral[(int64_t)i * E + e] = integ[i];
+    }
+    (void)KC;
+}
+
+template <int CTRL>
 __global__ void __launch_bounds__(kEnvThreads)
     compute_action_kernel(const __grid_constant__ qt_params P, const __grid_constant__ CtrlArgs A) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t E = A.E;
     if (e >= E) return;
-    constexpr int KC = LQI ? 9 : 6;
+    constexpr int KC = CtrlCols<CTRL>::value;
     double s[12], tp[3], tv[3], ta[3];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = A.obs[(int64_t)i * E + e];
@@ -187,20 +218,9 @@ __global__ void __launch_bounds__(kEnvThreads)
         tv[i] = A.obs[(int64_t)(15 + i) * E + e];
         ta[i] = A.obs[(int64_t)(18 + i) * E + e];
     }
-    double integ[3] = {0.0, 0.0, 0.0};
-    if (LQI && A.integral) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) integ[i] = A.integral[(int64_t)i * E + e];
-    }
-    const double err = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
-    int sat = 0;
     double act[4];
-    ctrl_action<LQI, true>(P, A.K + (e / A.k_stride) * 4 * KC, s, tp, tv, ta, err, integ, sat, act);
-    if (LQI && A.integral) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) A.integral[(int64_t)i * E + e] = integ[i];
-    }
-    if (A.saturation) A.saturation[e] += sat;
+    run_controller<CTRL>(P, A.K + (e / A.k_stride) * 4 * KC, E, e, s, tp, tv, ta, A.obs[(int64_t)21 * E + e],
+                         A.integral, A.saturation, act);
 #pragma unroll
     for (int i = 0; i < 4; i++) A.action[(int64_t)i * E + e] = act[i];
 }
@@ -219,10 +239,10 @@ struct StepArgs {
     double *info, *action_out;
 };
 
-template <int MOTION, bool LQI>
+template <int MOTION, int CTRL>
 __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, int64_t e) {
     const int64_t E = A.E;
-    constexpr int KC = LQI ? 9 : 6;
+    constexpr int KC = CtrlCols<CTRL>::value;
     double s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = A.state[(int64_t)i * E + e];
@@ -235,20 +255,8 @@ __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, 
 #pragma unroll
         for (int i = 0; i < 4; i++) act[i] = A.action_in[(int64_t)i * E + e];
     } else {
-        double integ[3] = {0.0, 0.0, 0.0};
-        if (LQI && A.integral) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) integ[i] = A.integral[(int64_t)i * E + e];
-        }
         tg.template state<true>(P, t, tp, tv, ta);
-        const double err = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
-        int sat = 0;
-        ctrl_action<LQI, true>(P, A.K + (e / A.k_stride) * 4 * KC, s, tp, tv, ta, err, integ, sat, act);
-        if (LQI && A.integral) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) A.integral[(int64_t)i * E + e] = integ[i];
-        }
-        if (A.saturation) A.saturation[e] += sat;
+        run_controller<CTRL>(P, A.K + (e / A.k_stride) * 4 * KC, E, e, s, tp, tv, ta, t, A.integral, A.saturation, act);
     }
     const int violated = validate_action(P, act, actv);
     DynConsts C;
@@ -299,17 +307,17 @@ __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, 
     }
 }
 
-template <bool LQI>
+template <int CTRL>
 __global__ void __launch_bounds__(kEnvThreads)
     step_kernel(const __grid_constant__ qt_params P, const __grid_constant__ StepArgs A) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A.E) return;
     switch (P.motion_type) {
-    case QT_MOTION_LINEAR: step_one<QT_MOTION_LINEAR, LQI>(P, A, e); break;
-    case QT_MOTION_CIRCULAR: step_one<QT_MOTION_CIRCULAR, LQI>(P, A, e); break;
-    case QT_MOTION_SINUSOIDAL: step_one<QT_MOTION_SINUSOIDAL, LQI>(P, A, e); break;
-    case QT_MOTION_FIGURE8: step_one<QT_MOTION_FIGURE8, LQI>(P, A, e); break;
-    default: step_one<QT_MOTION_STATIONARY, LQI>(P, A, e); break;
+    case QT_MOTION_LINEAR: step_one<QT_MOTION_LINEAR, CTRL>(P, A, e); break;
+    case QT_MOTION_CIRCULAR: step_one<QT_MOTION_CIRCULAR, CTRL>(P, A, e); break;
+    case QT_MOTION_SINUSOIDAL: step_one<QT_MOTION_SINUSOIDAL, CTRL>(P, A, e); break;
+    case QT_MOTION_FIGURE8: step_one<QT_MOTION_FIGURE8, CTRL>(P, A, e); break;
+    default: step_one<QT_MOTION_STATIONARY, CTRL>(P, A, e); break;
     }
 }
 
@@ -363,16 +371,17 @@ extern "C" int qt_compute_action_batched(qt_context *ctx, const qt_params *param
     if (!ctx) return QT_ERR_ARG;
     QT_REQUIRE(ctx, params && obs_dev && K_dev && action_out_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0, "E < 0");
-    QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, k_cols == expected_k_cols(*params), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
     QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
     if (E == 0) return QT_OK;
     if (k_stride < 1) k_stride = 1;
     CtrlArgs A{E, k_stride, obs_dev, K_dev, integral_io_dev, saturation_io_dev, action_out_dev};
     DeviceGuard guard(ctx->device);
-    if (params->use_lqi)
-        compute_action_kernel<true><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A);
-    else
-        compute_action_kernel<false><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A);
+    switch (ctrl_kind_of(*params)) {
+    case CK_PID: compute_action_kernel<CK_PID><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    case CK_LQI: compute_action_kernel<CK_LQI><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    default: compute_action_kernel<CK_LQR><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    }
     return check_launch(ctx, "compute_action_kernel");
 }
 
@@ -388,7 +397,7 @@ extern "C" int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t
     QT_REQUIRE(ctx, E >= 0, "E < 0");
     QT_REQUIRE(ctx, action_in_dev || K_dev, "either an action or a gain matrix is required");
     if (!action_in_dev) {
-        QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+        QT_REQUIRE(ctx, k_cols == expected_k_cols(*params), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
         QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
     }
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
@@ -398,9 +407,11 @@ extern "C" int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t
                K_dev, integral_io_dev, saturation_io_dev, obs_out_dev, reward_out_dev, done_out_dev,
                info_out_dev, action_out_dev};
     DeviceGuard guard(ctx->device);
-    if (params->use_lqi && !action_in_dev)
-        step_kernel<true><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A);
-    else
-        step_kernel<false><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A);
+    const int kind = action_in_dev ? CK_LQR : ctrl_kind_of(*params);
+    switch (kind) {
+    case CK_PID: step_kernel<CK_PID><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    case CK_LQI: step_kernel<CK_LQI><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    default: step_kernel<CK_LQR><<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(*params, A); break;
+    }
     return check_launch(ctx, "step_kernel");
 }

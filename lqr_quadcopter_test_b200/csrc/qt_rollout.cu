@@ -43,12 +43,12 @@ struct RolloutArgs {
 enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_MAX_ERR, CR_OV_CUR, CR_OV_MAX, CR_TARGET };
 constexpr int kColdRows = CR_TARGET + QT_TARGET_PARAMS;
 
-template <int MOTION, bool LQI, bool FULL>
+template <int MOTION, int CTRL, bool FULL>
 __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                    const __grid_constant__ RolloutArgs A) {
     extern __shared__ double smem[];
-    constexpr int KC = LQI ? 9 : 6;
+    constexpr int KC = CtrlCols<CTRL>::value;
     constexpr int T = kRolloutThreads;
     const int64_t E = A.E;
     const int64_t chain_id = (int64_t)blockIdx.x * T + threadIdx.x;
@@ -74,10 +74,14 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 
     double integ[3] = {0.0, 0.0, 0.0};
     int saturations = 0;
+    double last_time = __longlong_as_double(0x7ff8000000000000LL);  // PID: time of the previous call, NaN = none
     if (A.ctrl_state && A.chain > 1) {  // the controller object's state at the time of the call
 #pragma unroll
         for (int i = 0; i < 3; i++) integ[i] = A.ctrl_state[(int64_t)i * A.n_chains + chain_id];
-        saturations = (int)A.ctrl_state[3 * A.n_chains + chain_id];
+        if (CTRL == CK_PID)
+            last_time = A.ctrl_state[3 * A.n_chains + chain_id];
+        else
+            saturations = (int)A.ctrl_state[3 * A.n_chains + chain_id];
     }
 
     const int64_t first = chain_id * A.chain;
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         if (A.chain == 1) {  // controller.reset() before every episode (tuning.py:879)
             integ[0] = integ[1] = integ[2] = 0.0;
             saturations = 0;
+            last_time = __longlong_as_double(0x7ff8000000000000LL);
         }
 
         double t = 0.0;
@@ -123,7 +128,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         while (term == QT_TERM_NONE && step < A.max_steps) {
             // ---- controller on the pre-step observation
             double act[4];
-            ctrl_action<LQI, FULL>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
+            if constexpr (CTRL == CK_PID)
+                pid_action<FULL>(P, Kp, s, tp, tv, ta, t, integ, last_time, act);
+            else
+                ctrl_action<CTRL == CK_LQI, FULL>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
 
             // ---- metrics sample k = step (pre-step observation, eval.py:142-159)
             {
@@ -257,28 +265,31 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     if (A.ctrl_state) {
 #pragma unroll
         for (int i = 0; i < 3; i++) A.ctrl_state[(int64_t)i * A.n_chains + chain_id] = integ[i];
-        A.ctrl_state[3 * A.n_chains + chain_id] = (double)saturations;
+        A.ctrl_state[3 * A.n_chains + chain_id] = CTRL == CK_PID ? last_time : (double)saturations;
     }
 }
 
-template <int MOTION, bool LQI, bool FULL>
+template <int MOTION, int CTRL, bool FULL>
 static cudaError_t launch_one(const qt_params &P, const RolloutArgs &A, size_t smem, cudaStream_t st) {
     const int64_t blocks = (A.n_chains + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks <= 0) return cudaSuccess;
     DynConsts C;
     C.init(P);
-    rollout_kernel<MOTION, LQI, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, C, A);
+    rollout_kernel<MOTION, CTRL, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, C, A);
     return cudaGetLastError();
 }
 
 template <int MOTION>
 static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_t smem, bool full,
                                  cudaStream_t st) {
-    if (P.use_lqi)
-        return full ? launch_one<MOTION, true, true>(P, A, smem, st)
-                    : launch_one<MOTION, true, false>(P, A, smem, st);
-    return full ? launch_one<MOTION, false, true>(P, A, smem, st)
-                : launch_one<MOTION, false, false>(P, A, smem, st);
+    switch (ctrl_kind_of(P)) {
+    case CK_PID:
+        return full ? launch_one<MOTION, CK_PID, true>(P, A, smem, st) : launch_one<MOTION, CK_PID, false>(P, A, smem, st);
+    case CK_LQI:
+        return full ? launch_one<MOTION, CK_LQI, true>(P, A, smem, st) : launch_one<MOTION, CK_LQI, false>(P, A, smem, st);
+    default:
+        return full ? launch_one<MOTION, CK_LQR, true>(P, A, smem, st) : launch_one<MOTION, CK_LQR, false>(P, A, smem, st);
+    }
 }
 
 }  // namespace qt
@@ -295,7 +306,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     if (!ctx) return QT_ERR_ARG;
     QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
     QT_REQUIRE(ctx, E >= 0 && max_steps >= 0 && max_steps < (1ll << 31), "bad E / max_steps");
-    QT_REQUIRE(ctx, k_cols == (params->use_lqi ? 9 : 6), "k_cols must be 9 with use_lqi, else 6");
+    QT_REQUIRE(ctx, k_cols == expected_k_cols(*params), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
     QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
     QT_REQUIRE(ctx, (feat_out_dev == nullptr) == (act_out_dev == nullptr), "feat/act must come together");

@@ -27,7 +27,7 @@ def teacher_dataset(controller, env_config: EnvConfig | None = None, num_episode
     env_config = env_config or EnvConfig()
     ctx = _lib.get_context()
     seeds = torch.arange(num_episodes, dtype=torch.int64, device=ctx.device) + int(base_seed)
-    chain = 1 if (reset_controller_between_episodes or not controller.effective_use_lqi()) else max(num_episodes, 2)
+    chain = 1 if (reset_controller_between_episodes or not controller.carries_state()) else max(num_episodes, 2)
     out = rollout_device(controller, env_config, SuccessCriteria(), seeds, max_steps, chain=chain,
                          dataset_stride=stride, ctx=ctx)
     feats, acts = out["features"], out["actions"]

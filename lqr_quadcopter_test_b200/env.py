@@ -122,12 +122,12 @@ class BatchedQuadcopterEnv:
                 raise ValueError("step() needs either actions or a controller")
             a = None
             params = controller.kernel_params(self.config)
-            lqi = controller.effective_use_lqi()
-            k_cols = 9 if lqi else 6
+            k_cols = controller.k_cols()
             Kt = K if K is not None else torch.as_tensor(
                 np.ascontiguousarray(controller.effective_gain()), dtype=torch.float64, device=self.device)
-            if lqi and integral is None:
-                raise ValueError("LQI control inside step() needs the integral state tensor [3, E]")
+            if controller.carries_state() and integral is None:
+                raise ValueError("a stateful controller inside step() needs its state tensor "
+                                 "([3, E] LQI integrator, [4, E] PID integral + previous time)")
         self.ctx.step_batched(params, E, self.state, self.time, self.tparams, self.counters, a, Kt,
                               k_cols, E if K is None else 1, integral, saturation, self._obs, self._reward,
                               self._done, self._info, self._action)

@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from . import params as P
 from .config import EnvConfig
-from .controller import LQRController, RiccatiLQRController
+from .controller import LQRController, PIDController, RiccatiLQRController
 from .metrics import (EpisodeMetricsView, EvaluationSummary, SuccessCriteria, format_metrics_report,
                       summary_from_sums)
 
@@ -48,8 +48,7 @@ def rollout_device(controller, env_config: EnvConfig, criteria, seeds, max_steps
     dev = ctx.device
     E = int(seeds.numel())
     prm = controller.kernel_params(env_config, criteria)
-    lqi = controller.effective_use_lqi()
-    k_cols = 9 if lqi else 6
+    k_cols = controller.k_cols()
     if K is None:
         K = torch.as_tensor(np.ascontiguousarray(controller.effective_gain()), dtype=torch.float64, device=dev)
         k_stride = E
@@ -106,35 +105,32 @@ class Evaluator:
 
     # -- helpers ---------------------------------------------------------------------------------
     def _chain_for(self, n: int) -> int:
-        lqi = self.controller.effective_use_lqi()
-        carry = lqi and not self.reset_controller_between_episodes
+        carry = self.controller.carries_state() and not self.reset_controller_between_episodes
         return max(n, 2) if carry else 1  # chain > 1 <=> "do not reset, carry the state in"
 
     def _ctrl_state_in(self, n_chains: int):
-        """Device [4, n_chains] controller state: integrator + saturation count carried in."""
+        """Device [4, n_chains] controller state carried in (integrator + saturation count, or the
+        PID integral + time of its previous call)."""
         import torch
 
         ctx = _lib.get_context()
         st = torch.zeros((4, n_chains), dtype=torch.float64, device=ctx.device)
-        if n_chains == 1 and getattr(self.controller, "integral_state", None) is not None:
-            vals = list(np.asarray(self.controller.integral_state, dtype=np.float64)) + [
-                float(self.controller.get_saturation_count())]
-            st[:, 0] = torch.tensor(vals, dtype=torch.float64)
+        if n_chains == 1:
+            st[:, 0] = torch.from_numpy(np.asarray(self.controller.state_vector(), dtype=np.float64))
         return st
 
     def _ctrl_state_out(self, st, chain: int) -> None:
-        """Write the controller state back so the Python object ends where the reference's would."""
-        c = self.controller
+        """Write the controller state back so the Python object ends where the reference's would:
+        after one serial chain (chain > 1) in that chain's final state, otherwise (reset before every
+        episode) in the last episode's state with the saturation counts added up."""
         host = st.cpu().numpy()
-        lqi = getattr(c, "use_lqi", False) and getattr(c, "integral_state", None) is not None
-        if chain > 1:  # one serial chain that started from the controller's own state
-            if lqi:
-                c.integral_state = host[0:3, 0].copy()
-            c._saturation_count = int(host[3, 0])
-        else:  # reset before every episode: the object ends in the last episode's state
-            if lqi:
-                c.integral_state = host[0:3, -1].copy()
-            c._saturation_count = c.get_saturation_count() + int(host[3].sum())
+        if chain > 1:
+            self.controller.load_state_vector(host[:, 0], True)
+        else:
+            last = host[:, -1].copy()
+            if self.controller.name != "pid":
+                last[3] = host[3].sum()
+            self.controller.load_state_vector(last, False)
 
     @staticmethod
     def _episode_records(traj: np.ndarray, n_steps: int, target_radius: float) -> list[dict]:
@@ -286,7 +282,9 @@ def load_controller(controller_type: str, checkpoint_path: str | Path | None = N
         return RiccatiLQRController(config=lqi_config)
     if controller_type == "lqr":
         return LQRController(config=config)
-    if controller_type in ("pid", "deep"):
+    if controller_type == "pid":
+        return PIDController(config=config)
+    if controller_type in ("deep",):
         raise NotImplementedError(
             f"controller type '{controller_type}' is outside the accelerated Riccati-LQR/LQI path (DESIGN.md, scope)")
     raise ValueError(f"Unknown controller type: {controller_type}")

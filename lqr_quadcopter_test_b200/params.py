@@ -6,6 +6,7 @@ import ctypes as C
 
 from .config import EnvConfig
 
+CTRL_RICCATI, CTRL_PID = 0, 1
 MOTION_TYPES = {"stationary": 0, "linear": 1, "circular": 2, "sinusoidal": 3, "figure8": 4}
 INTEGRATORS = {"rk4": 0, "euler": 1}
 TERMINATION_REASONS = {0: "", 1: "time_limit", 2: "position_bounds", 3: "numerical_instability"}
@@ -43,7 +44,7 @@ class QtParams(C.Structure):
         ("ff_max_velocity", C.c_double), ("ff_max_acceleration", C.c_double),
         ("motion_type", C.c_int32), ("integrator", C.c_int32), ("use_lqi", C.c_int32),
         ("feedforward_enabled", C.c_int32), ("overshoot_window", C.c_int32),
-        ("reserved0", C.c_int32), ("reserved1", C.c_int32), ("reserved2", C.c_int32),
+        ("controller_type", C.c_int32), ("reserved1", C.c_int32), ("reserved2", C.c_int32),
     ]
 
     def copy(self) -> "QtParams":
@@ -103,6 +104,7 @@ def make_params(env_config: EnvConfig | None = None, controller=None, criteria=N
     p.integral_limit, p.integral_zero_threshold = 10.0, 0.01
     p.ff_max_velocity, p.ff_max_acceleration = 10.0, 5.0
     if controller is not None:
+        p.controller_type = CTRL_PID if getattr(controller, "name", "") == "pid" else CTRL_RICCATI
         p.ctrl_dt = controller.dt
         p.ctrl_hover_thrust = controller.hover_thrust
         p.ctrl_max_thrust, p.ctrl_min_thrust = controller.max_thrust, controller.min_thrust

@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 from . import params as P
 from .config import EnvConfig
-from .controller import LQRController, RiccatiLQRController, heuristic_lqr_gain
+from .controller import LQRController, PIDController, RiccatiLQRController, heuristic_lqr_gain
 from .metrics import SuccessCriteria
 
 logger = logging.getLogger(__name__)
@@ -218,8 +218,6 @@ class ControllerTuner:
                 import cma  # noqa: F401
             except ImportError:
                 raise ImportError("CMA-ES strategy requires the 'cma' package. Install it with: pip install cma")
-        if config.controller_type == "pid":
-            raise NotImplementedError("PID tuning is outside the accelerated Riccati-LQR/LQI path (DESIGN.md, scope)")
 
     # -- candidate generation: host, identical RNG consumption to tuning.py:662-735 -----------------
     def _draw(self, rng_def):
@@ -290,6 +288,8 @@ class ControllerTuner:
 
     # -- evaluation ----------------------------------------------------------------------------------
     def _create_controller(self, controller_config: dict):
+        if self.config.controller_type == "pid":
+            return PIDController(config=controller_config)
         if self.config.controller_type == "lqr":
             return LQRController(config=controller_config)
         if self.config.controller_type == "riccati_lqr":
@@ -338,7 +338,7 @@ class ControllerTuner:
 
         proto = self._create_controller(configs[0])
         C = len(configs)
-        if self.config.controller_type == "lqr" or len(configs) == 1:
+        if self.config.controller_type in ("pid", "lqr") or len(configs) == 1:
             ks = [np.ascontiguousarray(self._create_controller(c).effective_gain()) for c in configs] \
                 if C > 1 else [np.ascontiguousarray(proto.effective_gain())]
             return torch.as_tensor(np.stack(ks), dtype=torch.float64, device=ctx.device), proto
@@ -384,7 +384,6 @@ class ControllerTuner:
         env_config, criteria = self._env_and_criteria()
         K, proto = self._gains_for(configs, ctx)
         prm = proto.kernel_params(env_config, criteria)
-        lqi = proto.effective_use_lqi()
         f64 = dict(dtype=torch.float64, device=ctx.device)
         # every candidate sees the same episode seeds seed + ep (tuning.py:875)
         seeds = torch.arange(eps, dtype=torch.int64, device=ctx.device) + int(cfg.seed)
@@ -394,7 +393,7 @@ class ControllerTuner:
         tparams = tp.repeat(1, C).contiguous()
         E = C * eps
         metrics = torch.empty((16, E), **f64)
-        ctx.rollout(prm, E, int(cfg.evaluation_horizon), 1, state0, tparams, K.contiguous(), 9 if lqi else 6,
+        ctx.rollout(prm, E, int(cfg.evaluation_horizon), 1, state0, tparams, K.contiguous(), proto.k_cols(),
                     eps, metrics)
         cand = torch.empty((4, C), **f64)
         ctx.reduce_scores(metrics, C, eps, cand)

@@ -55,6 +55,10 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def k_cols_of(params: QtParams) -> int:
+    return 3 if params.controller_type == 1 else (9 if params.use_lqi else 6)
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -69,7 +73,7 @@ def rollout(params: QtParams, state0, tparams, K, k_stride=None, max_steps=3000,
     """Same contract as qt_rollout (include/qtrack.h).  Arrays are [F, E] float64."""
     state0, tparams, K = _f64(state0), _f64(tparams), _f64(K)
     E = state0.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     K = K.reshape(-1, 4, k_cols)
     if k_stride is None:
         k_stride = E if K.shape[0] == 1 else 1
@@ -106,7 +110,7 @@ def observe(params: QtParams, state, time, tparams):
 def compute_action(params: QtParams, obs, K, k_stride=None, integral=None, saturation=None):
     obs, K = _f64(obs), _f64(K)
     E = obs.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     if k_stride is None:
         k_stride = E
     act = np.zeros((4, E))
@@ -119,7 +123,7 @@ def step(params: QtParams, state, time, tparams, counters, action=None, K=None, 
          integral=None, saturation=None):
     """In-place env step on [12,E] state / [E] time / int64 [3,E] counters; returns outputs."""
     E = state.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     out = {"obs": np.zeros((22, E)), "reward": np.zeros(E), "done": np.zeros(E, dtype=np.int32),
            "info": np.zeros((4, E)), "action": np.zeros((4, E))}
     if action is not None:

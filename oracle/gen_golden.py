@@ -200,9 +200,13 @@ def run_reference_episode(env_cfg, controller, seed, criteria, max_steps=None, r
         step, info["time"], env._on_target_count, round(m.on_target_ratio * step), m.mean_tracking_error * step,
         m.max_tracking_error, m.rms_tracking_error ** 2 * step, m.total_control_effort, m.overshoot_count,
         m.max_overshoot, float(info.get("success", env._evaluate_success())), float(m.success), term,
-        info["action_violations"], controller.get_saturation_count(), info["tracking_error"]])
+        info["action_violations"], getattr(controller, "get_saturation_count", lambda: 0)(), info["tracking_error"]])
     extra = np.array([m.on_target_ratio, m.mean_tracking_error, m.rms_tracking_error, m.mean_control_effort])
-    integ = controller.integral_state.copy() if controller.integral_state is not None else np.zeros(3)
+    if hasattr(controller, "integral_error"):     # PID: integral + time of the previous call
+        integ = controller.integral_error.copy()
+    else:
+        integ = getattr(controller, "integral_state", None)
+        integ = integ.copy() if integ is not None else np.zeros(3)
     return dict(state0=state0, tparams=tp, metrics=vec, extra=extra, final_state=env.get_state_vector(),
                 samples=np.array(samples), integral=integ)
 
@@ -436,11 +440,130 @@ def gen_tuning():
     np.savez_compressed(OUT / "tuning.npz", **out)
 
 
+def gen_pid_lqr():
+    """§8(f).1: PID and the heuristic LQR through the same driver loops (pid_lqr.npz)."""
+    from quadcopter_tracking.controllers import LQRController, PIDController
+    from quadcopter_tracking.controllers.tuning import ControllerTuner, GainSearchSpace, TuningConfig
+    from quadcopter_tracking.env import EnvConfig
+    from quadcopter_tracking.eval import Evaluator, load_controller
+    from quadcopter_tracking.utils.metrics import SuccessCriteria
+
+    out = {}
+
+    def env_cfg(motion):
+        c = EnvConfig()
+        c.target.motion_type = motion
+        return c
+
+    pid_ki = {"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4}
+    pid_ff = {"feedforward_enabled": True, "ff_velocity_gain": [0.1, 0.1, 0.0], "ff_acceleration_gain": [0.05, 0.05, 0.0],
+              "ff_max_velocity": 0.9, "ff_max_acceleration": 0.4}
+    lqr_ff = {"feedforward_enabled": True, "ff_velocity_gain": 0.15, "ff_acceleration_gain": [0.05, 0.1, 0.0],
+              "ff_max_velocity": 0.8}
+    cases = [
+        ("pid_stationary", PIDController, "stationary", {}, list(range(42, 48)), None, True),
+        ("pid_linear", PIDController, "linear", {}, list(range(42, 48)), None, True),
+        ("pid_circular", PIDController, "circular", {}, list(range(42, 46)), None, True),
+        ("pid_sinusoidal", PIDController, "sinusoidal", {}, [42, 43], 1500, True),
+        ("pidki_linear", PIDController, "linear", pid_ki, list(range(42, 46)), None, True),
+        ("pidki_carry_stationary", PIDController, "stationary", pid_ki, [42, 43, 44], 1200, False),
+        ("pidff_circular", PIDController, "circular", pid_ff, list(range(42, 46)), None, True),
+        ("hlqr_linear", LQRController, "linear", {}, list(range(42, 48)), None, True),
+        ("hlqr_circular", LQRController, "circular", {"q_pos": [2e-4, 3e-4, 12.0], "r_rate": 1.5, "r_thrust": 0.7},
+         list(range(42, 46)), None, True),
+        ("hlqrff_sinusoidal", LQRController, "sinusoidal", lqr_ff, [42, 43], 1500, True),
+    ]
+    for name, cls, motion, ccfg, seeds, max_steps, reset_ctrl in cases:
+        controller = cls(config=ccfg)
+        recs = [run_reference_episode(env_cfg(motion), controller, s, SuccessCriteria(), max_steps, reset_ctrl)
+                for s in seeds]
+        out[f"{name}_seeds"] = np.array(seeds, dtype=np.uint64)
+        out[f"{name}_K"] = (np.stack([controller.kp_pos, controller.ki_pos, controller.kd_pos, np.zeros(3)]).astype(float)
+                            if cls is PIDController else controller.K)
+        for key in ("state0", "tparams", "metrics", "extra", "final_state", "integral"):
+            out[f"{name}_{key}"] = np.array([r[key] for r in recs]).T
+        out[f"{name}_samples"] = np.array([r["samples"] for r in recs])
+        if cls is PIDController:
+            out[f"{name}_last_time"] = np.array(np.nan if controller._last_time is None else controller._last_time)
+        print("  rollout", name, "done", flush=True)
+
+    # PID compute_action sequences on hand-made observations: times that advance, repeat and go back
+    rng = np.random.default_rng(12)
+
+    def obs_from(v):
+        return {"quadcopter": {"position": v[0:3], "velocity": v[3:6], "attitude": v[6:9], "angular_velocity": v[9:12]},
+                "target": {"position": v[12:15], "velocity": v[15:18], "acceleration": v[18:21]}, "time": float(v[21])}
+
+    for name, ccfg in (("seq_pid", {}), ("seq_pidki", {"ki_pos": [0.5, 0.4, 0.3], "integral_limit": 0.05}),
+                       ("seq_pidff", dict(pid_ff, ki_pos=0.2, integral_limit=2.0, kp_pos=1.5, kd_pos=[0.5, 0.6, 0.7]))):
+        c = PIDController(config=ccfg)
+        obs_rows, act_rows, int_rows, lt_rows = [], [], [], []
+        t = 0.0
+        for k in range(60):
+            v = rng.standard_normal(22) * np.array([2] * 3 + [3] * 3 + [0.3] * 6 + [2] * 3 + [3] * 3 + [4] * 3 + [1])
+            t = t + (0.01 if k % 11 else (-0.05 if k % 22 else 0.0))   # mostly forward; sometimes equal / backwards
+            v[21] = t
+            if k % 13 == 5:
+                v[15:18] *= 0.01
+                v[18:21] *= 0.01
+            a = c.compute_action(obs_from(v))
+            obs_rows.append(v)
+            act_rows.append([a["thrust"], a["roll_rate"], a["pitch_rate"], a["yaw_rate"]])
+            int_rows.append(c.integral_error.copy())
+            lt_rows.append(c._last_time)
+        out[f"{name}_obs"], out[f"{name}_act"] = np.array(obs_rows).T, np.array(act_rows).T
+        out[f"{name}_integral"], out[f"{name}_last_time"] = np.array(int_rows).T, np.array(lt_rows)
+        out[f"{name}_K"] = np.stack([c.kp_pos, c.ki_pos, c.kd_pos, np.zeros(3)]).astype(float)
+
+    # Evaluator with the PID / heuristic LQR (eval --controller pid|lqr): the controller is never reset
+    with tempfile.TemporaryDirectory() as td:
+        for ctype in ("pid", "lqr"):
+            cfg = EnvConfig()
+            cfg.target.motion_type = "linear"
+            ev = Evaluator(load_controller(ctype, config={}), cfg, SuccessCriteria(), output_dir=td)
+            s = ev.evaluate(num_episodes=4, base_seed=42, verbose=False)
+            out[f"eval_{ctype}_summary"] = np.array([
+                s.total_episodes, s.successful_episodes, s.success_rate, s.mean_on_target_ratio, s.std_on_target_ratio,
+                s.mean_tracking_error, s.std_tracking_error, s.mean_control_effort, s.best_episode_idx,
+                s.worst_episode_idx, float(s.meets_criteria)])
+            out[f"eval_{ctype}_ratios"] = np.array([m.on_target_ratio for m in s.episode_metrics])
+            out[f"eval_{ctype}_mean_err"] = np.array([m.mean_tracking_error for m in s.episode_metrics])
+
+    # tuner sweeps of tuning_pid_linear.yaml / tuning_lqr_linear.yaml (shortened)
+    spaces = {
+        "pid": GainSearchSpace(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]),
+                               kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])),
+        "pidki": GainSearchSpace(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]),
+                                 ki_pos_range=([0.0, 0.0, 0.0], [0.005, 0.005, 0.5]),
+                                 kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])),
+        "lqr": GainSearchSpace(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]),
+                               q_vel_range=([1e-3, 1e-3, 2.0], [1e-2, 1e-2, 8.0])),
+    }
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        for name, space in spaces.items():
+            tc = TuningConfig(controller_type="lqr" if name == "lqr" else "pid", search_space=space, strategy="random",
+                              max_iterations=5, evaluation_episodes=3, evaluation_horizon=400, seed=42,
+                              target_motion_type="linear", episode_length=4.0, output_dir="reports/tuning")
+            res = ControllerTuner(tc).tune()
+            keys = ("kp_pos", "ki_pos", "kd_pos") if name != "lqr" else ("q_pos", "q_vel")
+            out[f"tune_{name}_cfg"] = np.array([sum((r["config"].get(k, [0.0, 0.0, 0.0]) for k in keys), [])
+                                                for r in res.all_results])
+            out[f"tune_{name}_score"] = np.array([r["score"] for r in res.all_results])
+            out[f"tune_{name}_metrics"] = np.array([[r["metrics"]["mean_on_target_ratio"], r["metrics"]["mean_tracking_error"],
+                                                     r["metrics"]["success_rate"]] for r in res.all_results])
+            out[f"tune_{name}_best_score"] = np.array(res.best_score)
+            print("  tuning", name, "done", flush=True)
+    np.savez_compressed(OUT / "pid_lqr.npz", **out)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     _import_reference()
     cwd = os.getcwd()
-    for fn in (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts):
+    every = (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts, gen_pid_lqr)
+    chosen = [fn for fn in every if fn.__name__ in sys.argv[1:]] or every   # e.g. `gen_golden.py gen_pid_lqr`
+    for fn in chosen:
         print(fn.__name__, flush=True)
         fn()
         os.chdir(cwd)

@@ -90,9 +90,45 @@ def assert_rollout_matches(np, got: dict, npz, name: str, tol: float, sum_rtol: 
     """Compare a rollout result (metrics [16,E], final_state [12,E]) with the reference fixture."""
     M, G = got["metrics"], npz[name + "_metrics"]
     assert M.shape == G.shape
-    np.testing.assert_array_equal(M[COUNT_ROWS], G[COUNT_ROWS], err_msg=f"{name}: counters / flags")
+    # the reference's heuristic LQRController keeps no saturation counter (controllers/__init__.py:398-700)
+    count_rows = [r for r in COUNT_ROWS if not (name.startswith("hlqr") and r == P.M_SATURATIONS)]
+    np.testing.assert_array_equal(M[count_rows], G[count_rows], err_msg=f"{name}: counters / flags")
     np.testing.assert_allclose(M[SUM_ROWS], G[SUM_ROWS], rtol=max(sum_rtol, tol), atol=tol * 3000,
                                err_msg=f"{name}: per-episode sums")
     np.testing.assert_allclose(M[VALUE_ROWS], G[VALUE_ROWS], rtol=0, atol=tol, err_msg=f"{name}: values")
     np.testing.assert_allclose(got["final_state"], npz[name + "_final_state"], rtol=0, atol=tol,
                                err_msg=f"{name}: final state")
+
+
+# ---- §8(f).1: PID and heuristic-LQR fixtures (tests/golden/pid_lqr.npz) -----------------------------
+PID_KI = dict(integral_limit=0.4)
+PID_FF = dict(feedforward_enabled=True, ff_velocity_gain=[0.1, 0.1, 0.0], ff_acceleration_gain=[0.05, 0.05, 0.0],
+              ff_max_velocity=0.9, ff_max_acceleration=0.4)
+HLQR_FF = dict(feedforward_enabled=True, ff_velocity_gain=[0.15] * 3, ff_acceleration_gain=[0.05, 0.1, 0.0],
+               ff_max_velocity=0.8)
+PID_LQR_CASES = {
+    # name: (controller kwargs for controller_ns, max_steps, chain, constructor config of the drop-in class)
+    "pid_stationary": (dict(name="pid", integral_limit=0.0), 3002, 1, {}),
+    "pid_linear": (dict(name="pid", integral_limit=0.0), 3002, 1, {}),
+    "pid_circular": (dict(name="pid", integral_limit=0.0), 3002, 1, {}),
+    "pid_sinusoidal": (dict(name="pid", integral_limit=0.0), 1500, 1, {}),
+    "pidki_linear": (dict(name="pid", **PID_KI), 3002, 1, {"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4}),
+    "pidki_carry_stationary": (dict(name="pid", **PID_KI), 1200, 3,
+                               {"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4}),
+    "pidff_circular": (dict(name="pid", integral_limit=0.0, **PID_FF), 3002, 1,
+                       {"feedforward_enabled": True, "ff_velocity_gain": [0.1, 0.1, 0.0],
+                        "ff_acceleration_gain": [0.05, 0.05, 0.0], "ff_max_velocity": 0.9, "ff_max_acceleration": 0.4}),
+    "hlqr_linear": (dict(), 3002, 1, {}),
+    "hlqr_circular": (dict(), 3002, 1, {"q_pos": [2e-4, 3e-4, 12.0], "r_rate": 1.5, "r_thrust": 0.7}),
+    "hlqrff_sinusoidal": (dict(**HLQR_FF), 1500, 1,
+                          {"feedforward_enabled": True, "ff_velocity_gain": 0.15,
+                           "ff_acceleration_gain": [0.05, 0.1, 0.0], "ff_max_velocity": 0.8}),
+}
+
+
+def pid_lqr_case(name: str):
+    """-> (qt_params, max_steps, chain, tolerance, constructor config, env config)."""
+    kw, max_steps, chain, cfg = PID_LQR_CASES[name]
+    env = EnvConfig()
+    env.target.motion_type = name.split("_")[-1]
+    return P.make_params(env, controller_ns(**kw), SuccessCriteria()), max_steps, chain, TOL_LQR, cfg, env

@@ -12,6 +12,10 @@ def ctx():
     return _lib.get_context()
 
 
+def k_cols_of(params) -> int:
+    return 3 if params.controller_type == 1 else (9 if params.use_lqi else 6)
+
+
 def dev(a, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=ctx().device).contiguous()
 
@@ -30,7 +34,7 @@ def rollout(params, state0, tparams, K, k_stride=None, max_steps=3000, chain=1, 
             want_final_state=True, traj_stride=0, data_stride=0):
     c = ctx()
     E = state0.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     Kt = dev(np.asarray(K).reshape(-1, 4, k_cols))
     if k_stride is None:
         k_stride = E if Kt.shape[0] == 1 else 1
@@ -67,7 +71,7 @@ def observe(params, state, time, tparams):
 def compute_action(params, obs, K, k_stride=None, integral=None, saturation=None):
     c = ctx()
     E = obs.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     act = torch.zeros((4, E), dtype=torch.float64, device=c.device)
     it = dev(integral) if integral is not None else None
     st = dev(saturation, torch.int64) if saturation is not None else None
@@ -83,7 +87,7 @@ def step(params, state, time, tparams, counters, action=None, K=None, k_stride=N
          saturation=None):
     c = ctx()
     E = state.shape[1]
-    k_cols = 9 if params.use_lqi else 6
+    k_cols = k_cols_of(params)
     f64 = dict(dtype=torch.float64, device=c.device)
     st, tm, cn = dev(state), dev(time), dev(counters, torch.int64)
     out = {"obs": torch.zeros((22, E), **f64), "reward": torch.zeros(E, **f64),

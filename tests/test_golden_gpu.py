@@ -209,3 +209,117 @@ def test_tuner_matches_reference(golden, tmp_path):
         assert abs(res.best_score - float(g[key + "_best_score"])) < 1e-10
         assert res.best_config == res.all_results[int(g[key + "_best"])]["config"]
         assert res.iterations_completed == 5 and list((tmp_path / key).glob("*_results.json"))
+
+
+# ---- §8(f).1: PID and heuristic LQR in the same kernels --------------------------------------------
+def test_pid_and_heuristic_lqr_rollouts_match_reference(golden, gb):
+    g = golden["pid_lqr"]
+    for name in gc.PID_LQR_CASES:
+        prm, max_steps, chain, tol, _cfg, _env = gc.pid_lqr_case(name)
+        pid = name.startswith("pid")
+        cs = np.zeros((4, 1)) if chain > 1 else None
+        if cs is not None:
+            cs[3] = np.nan
+        out = gb.rollout(prm, g[name + "_state0"], g[name + "_tparams"], g[name + "_K"], max_steps=max_steps,
+                         chain=chain, ctrl_state=cs, traj_stride=250)
+        gc.assert_rollout_matches(np, out, g, name, tol)
+        samples = g[name + "_samples"]
+        n_s = samples.shape[1]
+        got = np.transpose(out["traj"][:n_s, P.TRAJ_STATE:P.TRAJ_STATE + 12, :], (2, 0, 1))
+        np.testing.assert_allclose(got, samples, rtol=0, atol=tol, err_msg=name)
+        if pid and chain > 1:
+            np.testing.assert_allclose(cs[0:3, 0], g[name + "_integral"][:, -1], rtol=0, atol=tol)
+            assert cs[3, 0] == float(g[name + "_last_time"])
+        elif pid:
+            cs1 = np.zeros((4, samples.shape[0]))
+            gb.rollout(prm, g[name + "_state0"], g[name + "_tparams"], g[name + "_K"], max_steps=max_steps,
+                       ctrl_state=cs1)
+            np.testing.assert_allclose(cs1[0:3], g[name + "_integral"], rtol=0, atol=tol, err_msg=name)
+
+
+@pytest.mark.parametrize("name", ["seq_pid", "seq_pidki", "seq_pidff"])
+def test_pid_controller_matches_reference(golden, gb, name):
+    """controllers/__init__.py:243-379 one call at a time: dt from observation times (forward,
+    equal and backwards), integral clamp, feedforward clamps."""
+    g = golden["pid_lqr"]
+    kw = {"seq_pid": dict(integral_limit=0.0), "seq_pidki": dict(integral_limit=0.05),
+          "seq_pidff": dict(integral_limit=2.0, **gc.PID_FF)}[name]
+    prm = P.make_params(EnvConfig(), gc.controller_ns(name="pid", **kw))
+    obs, K = g[f"{name}_obs"], g[f"{name}_K"]
+    state = np.zeros((4, 1))
+    state[3] = np.nan
+    for k in range(obs.shape[1]):
+        act = gb.compute_action(prm, obs[:, k:k + 1], K, integral=state)
+        np.testing.assert_allclose(act[:, 0], g[f"{name}_act"][:, k], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(state[0:3, 0], g[f"{name}_integral"][:, k], rtol=0, atol=1e-15)
+        assert state[3, 0] == g[f"{name}_last_time"][k]
+
+
+def test_pid_dropin_class_matches_reference_sequence(golden, gpu_ctx):
+    """PIDController.compute_action(obs dict) through the public class, state kept in the object."""
+    from lqr_quadcopter_test_b200 import PIDController
+
+    g = golden["pid_lqr"]
+    c = PIDController(config=dict(gc.PID_LQR_CASES["pidff_circular"][3], ki_pos=0.2, integral_limit=2.0, kp_pos=1.5,
+                                  kd_pos=[0.5, 0.6, 0.7]))
+    obs = g["seq_pidff_obs"]
+    for k in range(obs.shape[1]):
+        v = obs[:, k]
+        a = c.compute_action({"quadcopter": {"position": v[0:3], "velocity": v[3:6], "attitude": v[6:9],
+                                             "angular_velocity": v[9:12]},
+                              "target": {"position": v[12:15], "velocity": v[15:18], "acceleration": v[18:21]},
+                              "time": float(v[21])})
+        np.testing.assert_allclose([a["thrust"], a["roll_rate"], a["pitch_rate"], a["yaw_rate"]],
+                                   g["seq_pidff_act"][:, k], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(c.integral_error, g["seq_pidff_integral"][:, k], rtol=0, atol=1e-15)
+        assert c._last_time == g["seq_pidff_last_time"][k]
+    c.reset()
+    assert c._last_time is None and not c.integral_error.any()
+
+
+@pytest.mark.parametrize("ctype", ["pid", "lqr"])
+def test_evaluator_pid_and_lqr_match_reference(golden, tmp_path, ctype):
+    """`eval --controller pid|lqr --motion-type linear` (Makefile compare-controllers)."""
+    from lqr_quadcopter_test_b200 import EnvConfig as EC, Evaluator, SuccessCriteria, load_controller
+
+    g = golden["pid_lqr"]
+    cfg = EC()
+    cfg.target.motion_type = "linear"
+    ev = Evaluator(load_controller(ctype, config={}), cfg, SuccessCriteria(), output_dir=tmp_path)
+    s = ev.evaluate(num_episodes=4, base_seed=42, verbose=False)
+    ref = g[f"eval_{ctype}_summary"]
+    assert (s.total_episodes, s.successful_episodes, s.success_rate) == (int(ref[0]), int(ref[1]), ref[2])
+    assert abs(s.mean_on_target_ratio - ref[3]) < 1e-14 and abs(s.std_on_target_ratio - ref[4]) < 1e-13
+    assert abs(s.mean_tracking_error - ref[5]) < 1e-10 and abs(s.std_tracking_error - ref[6]) < 1e-10
+    assert abs(s.mean_control_effort - ref[7]) < 1e-9
+    assert (s.best_episode_idx, s.worst_episode_idx, s.meets_criteria) == (int(ref[8]), int(ref[9]), bool(ref[10]))
+    np.testing.assert_array_equal([m.on_target_ratio for m in s.episode_metrics], g[f"eval_{ctype}_ratios"])
+    np.testing.assert_allclose([m.mean_tracking_error for m in s.episode_metrics], g[f"eval_{ctype}_mean_err"],
+                               rtol=0, atol=1e-10)
+
+
+def test_pid_and_lqr_tuner_matches_reference(golden, tmp_path):
+    """tuning_pid_linear.yaml / tuning_lqr_linear.yaml (shortened): sampling order, rollout, scores."""
+    from lqr_quadcopter_test_b200 import ControllerTuner, GainSearchSpace, TuningConfig
+
+    g = golden["pid_lqr"]
+    spaces = {
+        "pid": dict(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]), kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])),
+        "pidki": dict(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]), ki_pos_range=([0.0, 0.0, 0.0], [0.005, 0.005, 0.5]),
+                      kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])),
+        "lqr": dict(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), q_vel_range=([1e-3, 1e-3, 2.0], [1e-2, 1e-2, 8.0])),
+    }
+    for key, kw in spaces.items():
+        tc = TuningConfig(controller_type="lqr" if key == "lqr" else "pid", search_space=GainSearchSpace(**kw),
+                          strategy="random", max_iterations=5, evaluation_episodes=3, evaluation_horizon=400, seed=42,
+                          target_motion_type="linear", episode_length=4.0, output_dir=str(tmp_path / key))
+        res = ControllerTuner(tc).tune()
+        keys = ("kp_pos", "ki_pos", "kd_pos") if key != "lqr" else ("q_pos", "q_vel")
+        cfgs = np.array([sum((r["config"].get(k, [0.0, 0.0, 0.0]) for k in keys), []) for r in res.all_results])
+        np.testing.assert_array_equal(cfgs, g[f"tune_{key}_cfg"])
+        scores = np.array([r["score"] for r in res.all_results])
+        np.testing.assert_allclose(scores, g[f"tune_{key}_score"], rtol=0, atol=1e-10, err_msg=key)
+        met = np.array([[r["metrics"]["mean_on_target_ratio"], r["metrics"]["mean_tracking_error"],
+                         r["metrics"]["success_rate"]] for r in res.all_results])
+        np.testing.assert_allclose(met, g[f"tune_{key}_metrics"], rtol=0, atol=1e-10, err_msg=key)
+        assert abs(res.best_score - float(g[f"tune_{key}_best_score"])) < 1e-10

@@ -118,8 +118,7 @@ def test_grid_candidates_match_the_reference(golden, tmp_path):
 
 
 def test_tuner_rejects_what_is_out_of_scope(tmp_path):
-    with pytest.raises(NotImplementedError):
-        ControllerTuner(TuningConfig(controller_type="pid", output_dir=str(tmp_path)))
+    ControllerTuner(TuningConfig(controller_type="pid", output_dir=str(tmp_path)))   # §8(f).1: in scope now
     with pytest.raises(ImportError, match="cma"):
         ControllerTuner(TuningConfig(controller_type="riccati_lqr", strategy="cma_es", output_dir=str(tmp_path)))
     with pytest.raises(ValueError, match="traversal"):

@@ -166,3 +166,71 @@ def test_config1_summary_matches_reference(golden):
         np.testing.assert_allclose(row[P.TRAJ_TARGET_P:P.TRAJ_TARGET_P + 6], rec[7:13], rtol=0, atol=1e-13)
         np.testing.assert_allclose(row[P.TRAJ_ACTION:P.TRAJ_ACTION + 4], rec[13:17], rtol=0, atol=1e-13)
         np.testing.assert_allclose(row[P.TRAJ_ERR], rec[18], rtol=0, atol=1e-13)
+
+
+# ---- §8(f).1: PID and heuristic LQR ----------------------------------------------------------------
+def test_pid_and_heuristic_lqr_rollouts_match_reference(golden):
+    g = golden["pid_lqr"]
+    for name in gc.PID_LQR_CASES:
+        prm, max_steps, chain, _tol, _cfg, _env = gc.pid_lqr_case(name)
+        pid = name.startswith("pid")
+        cs = np.zeros((4, 1)) if chain > 1 else None
+        if cs is not None:
+            cs[3] = np.nan            # PIDController._last_time is None
+        out = oracle.rollout(prm, g[name + "_state0"], g[name + "_tparams"], g[name + "_K"], max_steps=max_steps,
+                             chain=chain, ctrl_state=cs, traj_stride=250)
+        gc.assert_rollout_matches(np, out, g, name, tol=2e-11, sum_rtol=1e-13)
+        samples = g[name + "_samples"]
+        n_s = samples.shape[1]
+        got = out["traj"][:n_s, P.TRAJ_STATE:P.TRAJ_STATE + 12, :]
+        np.testing.assert_allclose(np.transpose(got, (2, 0, 1)), samples, rtol=0, atol=2e-11, err_msg=name)
+        if pid and chain > 1:      # Evaluator semantics: integral and _last_time carry over
+            np.testing.assert_allclose(cs[0:3, 0], g[name + "_integral"][:, -1], rtol=0, atol=1e-12)
+            assert cs[3, 0] == float(g[name + "_last_time"])
+        elif pid:
+            cs1 = np.zeros((4, samples.shape[0]))
+            oracle.rollout(prm, g[name + "_state0"], g[name + "_tparams"], g[name + "_K"], max_steps=max_steps,
+                           ctrl_state=cs1)
+            np.testing.assert_allclose(cs1[0:3], g[name + "_integral"], rtol=0, atol=1e-12, err_msg=name)
+
+
+@pytest.mark.parametrize("name", ["seq_pid", "seq_pidki", "seq_pidff"])
+def test_pid_controller_matches_reference(golden, name):
+    g = golden["pid_lqr"]
+    kw = {"seq_pid": dict(integral_limit=0.0), "seq_pidki": dict(integral_limit=0.05),
+          "seq_pidff": dict(integral_limit=2.0, **gc.PID_FF)}[name]
+    prm = P.make_params(EnvConfig(), gc.controller_ns(name="pid", **kw))
+    obs, K = g[f"{name}_obs"], g[f"{name}_K"]
+    state = np.zeros((4, 1))
+    state[3] = np.nan
+    for k in range(obs.shape[1]):
+        act = oracle.compute_action(prm, obs[:, k:k + 1], K, integral=state)
+        np.testing.assert_allclose(act[:, 0], g[f"{name}_act"][:, k], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(state[0:3, 0], g[f"{name}_integral"][:, k], rtol=0, atol=1e-15)
+        assert state[3, 0] == g[f"{name}_last_time"][k]
+
+
+def test_pid_and_lqr_tuner_scores_match_reference(golden):
+    """tuning.py:846-928 for controller_type pid / lqr (tuning_pid_linear.yaml, tuning_lqr_linear.yaml)."""
+    from lqr_quadcopter_test_b200.controller import heuristic_lqr_gain
+    from lqr_quadcopter_test_b200.metrics import SuccessCriteria
+
+    g = golden["pid_lqr"]
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    env.simulation.max_episode_time = 4.0
+    crit = SuccessCriteria(0.8, 4.0, 0.5)
+    for key in ("pid", "pidki", "lqr"):
+        cfgs = g[f"tune_{key}_cfg"]
+        C_, eps = cfgs.shape[0], 3
+        if key == "lqr":
+            prm = P.make_params(env, gc.controller_ns(), crit)
+            Ks = np.array([heuristic_lqr_gain(c[0:3], c[3:6], 1.0, 1.0) for c in cfgs])
+        else:
+            prm = P.make_params(env, gc.controller_ns(name="pid", integral_limit=0.0), crit)
+            Ks = np.array([np.concatenate([c.reshape(3, 3), np.zeros((1, 3))]) for c in cfgs])  # kp | ki | kd | 0
+        s0, tp = oracle.reset_reference(prm, [42, 43, 44])
+        out = oracle.rollout(prm, np.tile(s0, (1, C_)), np.tile(tp, (1, C_)), Ks, k_stride=eps, max_steps=400)
+        cand = oracle.reduce_scores(out["metrics"], C_, eps)
+        np.testing.assert_allclose(cand[0], g[f"tune_{key}_score"], rtol=0, atol=1e-12, err_msg=key)
+        np.testing.assert_allclose(cand[1:4].T, g[f"tune_{key}_metrics"], rtol=0, atol=1e-12, err_msg=key)
