@@ -61,6 +61,10 @@ enum qt_integrator { QT_INTEGRATOR_RK4 = 0, QT_INTEGRATOR_EULER = 1 }; /* quadco
  *                    gains: row-major [4][3] = kp | ki | kd | (unused row)                         */
 enum qt_controller { QT_CTRL_RICCATI = 0, QT_CTRL_PID = 1 };
 
+/* qt_params.debug_flags.  QT_DEBUG_GENERAL_PATH: qt_rollout always runs the general step loop, never
+ * the structure-exploiting one (zero yaw, axis-decoupled gain); results must not change (tests).  */
+#define QT_DEBUG_GENERAL_PATH 1
+
 /* quadcopter_env.py:513-535; 0 = the step cap ended the loop, not the environment */
 enum qt_termination {
     QT_TERM_NONE = 0,
@@ -138,7 +142,8 @@ typedef struct qt_params {
     int32_t feedforward_enabled;  /* riccati_lqr.py:494                                     */
     int32_t overshoot_window;     /* metrics.py:208, default 10                             */
     int32_t controller_type;      /* enum qt_controller                                     */
-    int32_t reserved1, reserved2;
+    int32_t debug_flags;          /* QT_DEBUG_* bits; 0 in production                       */
+    int32_t reserved2;
 } qt_params;
 
 typedef struct qt_context qt_context;

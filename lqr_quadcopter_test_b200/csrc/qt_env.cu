@@ -269,7 +269,7 @@ __device__ __forceinline__ void step_one(const qt_params &P, const StepArgs &A, 
     t += P.dt;
     tg.template state<true>(P, t, tp, tv, ta);
     const double err = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
-    const int term = termination_code(P, s, t);
+    const int term = termination_code(P, C, s, t);
     const bool on = err <= P.env_target_radius;
     const int64_t steps = A.counters[0 * E + e] + 1;
     const int64_t on_count = A.counters[1 * E + e] + (on ? 1 : 0);

@@ -13,6 +13,8 @@
 // the FULL variant only, for the optional strided trajectory log / teacher data set, which are
 // written struct-of-arrays so a warp's stores are contiguous.  The kernel is bound by the FP64
 // pipe; there is no GEMM-shaped work and no use for tensor cores.
+#include <type_traits>
+
 #include "qt_common.cuh"
 #include "qt_step.cuh"
 
@@ -125,13 +127,36 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             trig_full(e0, B);
         }
 
+        // ---- structure test (once per episode).  Every design the reference itself produces (PID,
+        // heuristic LQR, Riccati-LQR/LQI with diagonal Q and R) commands a yaw rate of exactly zero
+        // through an axis-decoupled gain, and reset() starts with zero yaw: yaw then stays exactly
+        // zero and the products with the zero gain entries vanish.  The FAST instantiation of the
+        // step loop skips that arithmetic; it is bit-identical to the general one (up to the sign
+        // of exact zeros) and is only entered when the whole warp qualifies, so the two loop bodies
+        // never diverge inside a warp.  params.debug_flags bit 0 forces the general path (tests).
+        bool fast = !(P.debug_flags & QT_DEBUG_GENERAL_PATH) && s[8] == 0.0 && s[11] == 0.0;
+        {
+            int hmax = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) hmax = max(hmax, hi_abs(s[i]));
+#pragma unroll
+            for (int i = 0; i < TargetParamCount<MOTION>::value; i++) hmax = max(hmax, hi_abs(cold[(CR_TARGET + i) * T]));
+#pragma unroll
+            for (int i = 0; i < 3; i++) hmax = max(hmax, hi_abs(integ[i]));
+            fast = fast && hmax < 0x7ff00000;  // 0 * inf would differ from the dense products
+            if constexpr (CTRL != CK_PID) fast = fast && gain_is_axis_decoupled<CTRL == CK_LQI>(Kp);
+        }
+        const bool warp_fast = __all_sync(__activemask(), fast);
+
+        auto step_loop = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
         while (term == QT_TERM_NONE && step < A.max_steps) {
             // ---- controller on the pre-step observation
             double act[4];
             if constexpr (CTRL == CK_PID)
                 pid_action<FULL>(P, Kp, s, tp, tv, ta, t, integ, last_time, act);
             else
-                ctrl_action<CTRL == CK_LQI, FULL>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
+                ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
 
             // ---- metrics sample k = step (pre-step observation, eval.py:142-159)
             {
@@ -205,15 +230,15 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             double actv[4], eta_old[3];
             violations += A.env_bounds_check ? validate_action<true>(P, act, actv) : validate_action<false>(P, act, actv);
             if (euler)
-                integrate<true>(C, s, actv, B, eta_old);
+                integrate<true, FAST>(C, s, actv, B, eta_old);
             else
-                integrate<false>(C, s, actv, B, eta_old);
-            constrain_state(P, C, s);
-            trig_rebase(eta_old, s, (step & 15) == 15, B);
+                integrate<false, FAST>(C, s, actv, B, eta_old);
+            constrain_state<FAST>(P, C, s);
+            trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
             t += C.dt;
             tg.template state<FULL>(P, t, tp, tv, ta);
             err_post = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
-            term = termination_code(P, s, t);
+            term = termination_code(P, C, s, t);
             env_on += (err_post <= P.env_target_radius) ? 1 : 0;
             if constexpr (FULL) {
                 if (log_traj) {
@@ -227,6 +252,11 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             step += 1;
             err_pre = err_post;
         }
+        };
+        if (warp_fast)
+            step_loop(std::true_type{});
+        else
+            step_loop(std::false_type{});
         double ov_max = cold[CR_OV_MAX * T];
         if (in_phase && streak >= P.overshoot_window) {
             ov_count += 1;

@@ -59,6 +59,7 @@ QT_TRIG_CONST double c_trig[32] = {
 
 constexpr double kShiftMax = 0.26;        // full Taylor polynomials: truncation error < 1e-17 up to here
 constexpr double kShiftSmall = 0.0078125;  // 2^-7: sin through d^5, cos through d^6 suffice (< 4e-19)
+constexpr double kShiftTiny = 0.0009765625;  // 2^-10: sin through d^3, cos through d^4 suffice (< 8e-18)
 
 // Out-of-line so the (practically never taken) huge-argument path costs the hot loop one
 // predicated call instead of an inlined Payne-Hanek reduction.
@@ -109,12 +110,20 @@ QT_TRIG_FN void sincos_pi(double x, double &s, double &c) {
 // sin/cos of `arg`, given sin/cos of `base`, where arg = fl(base + small increment) and the
 // caller guarantees |arg - base| <= kShiftMax (SMALL = false) or <= kShiftSmall (SMALL = true:
 // two Taylor terms fewer per polynomial, truncation error < 4e-19).
-template <bool SMALL>
+// TIER 0: |d| <= kShiftMax, 1: |d| <= kShiftSmall, 2: |d| <= kShiftTiny
+template <int TIER>
 QT_TRIG_FN void sincos_shifted(double base, double sb, double cb, double arg, double &s, double &c) {
     const double d = arg - base;  // exact (Sterbenz) or the increment itself when base is tiny
     const double z = d * d;
+    if (TIER == 2) {
+        const double sd = fma(d * z, c_trig[16], d);              // d - d^3/6
+        const double cm = z * fma(z, c_trig[22], c_trig[21]);     // -z/2 + z^2/24
+        s = fma(cb, sd, fma(sb, cm, sb));
+        c = fma(-sb, sd, fma(cb, cm, cb));
+        return;
+    }
     double p, q;
-    if (SMALL) {
+    if (TIER == 1) {
         p = fma(z, c_trig[17], c_trig[16]);
         q = fma(z, c_trig[23], c_trig[22]);
     } else {

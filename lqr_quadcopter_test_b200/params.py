@@ -44,7 +44,7 @@ class QtParams(C.Structure):
         ("ff_max_velocity", C.c_double), ("ff_max_acceleration", C.c_double),
         ("motion_type", C.c_int32), ("integrator", C.c_int32), ("use_lqi", C.c_int32),
         ("feedforward_enabled", C.c_int32), ("overshoot_window", C.c_int32),
-        ("controller_type", C.c_int32), ("reserved1", C.c_int32), ("reserved2", C.c_int32),
+        ("controller_type", C.c_int32), ("debug_flags", C.c_int32), ("reserved2", C.c_int32),
     ]
 
     def copy(self) -> "QtParams":

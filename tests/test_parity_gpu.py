@@ -262,3 +262,50 @@ def test_full_size_properties_one_million_linear_episodes(golden, gb):
     g = golden["rollouts"]
     np.testing.assert_allclose(out["final_state"][:, :8].cpu().numpy(), g["lqr_linear_final_state"], rtol=0, atol=gc.TOL_LQR)
     np.testing.assert_array_equal(M[gc.COUNT_ROWS][:, :8].cpu().numpy(), g["lqr_linear_metrics"][gc.COUNT_ROWS])
+
+
+def _axis_decoupled(K):
+    """K with everything outside the z->thrust / y->roll / x->pitch pattern set to exactly zero
+    (what the SDA solver returns for the reference's diagonal designs; scipy leaves ~1e-14 there)."""
+    K = np.array(K, dtype=np.float64)
+    keep = np.zeros_like(K, dtype=bool)
+    for c in range(K.shape[1]):
+        keep[{2: 0, 1: 1, 0: 2}[c % 3], c] = True
+    return np.where(keep, K, 0.0)
+
+
+@pytest.mark.parametrize("motion", ["linear", "sinusoidal"])
+@pytest.mark.parametrize("mode", ["lqr", "lqi", "pid", "lqr_ff_data"])
+def test_structure_exploiting_path_is_identical_to_the_general_path(golden, gb, orc, motion, mode):
+    """qt_rollout's FAST step loop (zero yaw, axis-decoupled gain) against the general loop forced by
+    QT_DEBUG_GENERAL_PATH: every output identical; and against the oracle with the same gain."""
+    E = 1024
+    env = EnvConfig()
+    env.target.motion_type = motion
+    kw = {"lqr": {}, "lqi": dict(use_lqi=True), "pid": dict(name="pid", integral_limit=0.3),
+          "lqr_ff_data": dict(feedforward_enabled=True, ff_velocity_gain=[0.1, 0.1, 0.0], ff_acceleration_gain=[0.05, 0.05, 0.0])}[mode]
+    prm = P.make_params(env, gc.controller_ns(**kw))
+    if mode == "pid":
+        K = np.array([[0.01, 0.01, 4.0], [0.002, 0.002, 0.3], [0.06, 0.06, 2.0], [0.0, 0.0, 0.0]])
+    else:
+        K = _axis_decoupled(_gains(golden, mode == "lqi"))
+    s0, tp = orc.reset_reference(prm, np.arange(7_000, 7_000 + E))
+    extra = dict(traj_stride=500, data_stride=700) if mode == "lqr_ff_data" else dict(traj_stride=500)
+    fast = gb.rollout(prm, s0, tp, K, max_steps=3002, **extra)
+    gen_prm = prm.copy()
+    gen_prm.debug_flags = 1
+    general = gb.rollout(gen_prm, s0, tp, K, max_steps=3002, **extra)
+    for key in fast:
+        np.testing.assert_array_equal(fast[key], general[key], err_msg=f"{mode}/{motion}: {key}")
+    ref = orc.rollout(prm, s0, tp, K, max_steps=3002, n_threads=8)
+    _compare_rollouts(fast, ref, gc.TOL_LQI if mode == "lqi" else gc.TOL_LQR, f"fast {mode}/{motion}")
+    # a warp that holds one episode with a non-zero yaw (or a dense gain) must take the general path
+    s0b = s0.copy()
+    s0b[8, 5::64] = 0.3
+    s0b[11, 9::64] = -0.2
+    mixed = gb.rollout(prm, s0b, tp, K, max_steps=600)
+    mixed_general = gb.rollout(gen_prm, s0b, tp, K, max_steps=600)
+    for key in mixed:
+        np.testing.assert_array_equal(mixed[key], mixed_general[key], err_msg=f"{mode}/{motion} mixed: {key}")
+    ref_b = orc.rollout(prm, s0b, tp, K, max_steps=600, n_threads=8)
+    _compare_rollouts(mixed, ref_b, gc.TOL_LQI if mode == "lqi" else gc.TOL_LQR, f"mixed {mode}/{motion}")

@@ -1,0 +1,88 @@
+"""Build A/B variants of libqtrack.so (one per -D setting) into lqr_quadcopter_test_b200/variants/
+and, on the GPU box, time the headline rollout with each:
+
+    python tools/ab_variants.py build  name1:-DQT_X=0  name2:-DQT_Y=1,-DQT_Z=0 ...
+    python tools/ab_variants.py run [E]      # every variants/libqtrack_*.so + the default library
+"""
+import os
+import pathlib
+import subprocess
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+VAR = ROOT / "lqr_quadcopter_test_b200" / "variants"
+sys.path.insert(0, str(ROOT))
+
+
+def build(specs):
+    from lqr_quadcopter_test_b200 import build as qb
+
+    VAR.mkdir(exist_ok=True)
+    for old in VAR.glob("libqtrack_*.so"):
+        old.unlink()
+    nvcc = qb._nvcc()
+    for spec in specs:
+        name, flags = spec.split(":", 1)
+        flags = [f for f in flags.split(",") if f]
+        objs = []
+        tmp = VAR / f"obj_{name}"
+        tmp.mkdir(exist_ok=True)
+        procs = []
+        for src in qb.SOURCES:
+            o = tmp / (src + ".o")
+            objs.append(str(o))
+            procs.append(subprocess.Popen([nvcc, *qb.NVCC_FLAGS, *flags, "-c", str(qb.CSRC / src), "-o", str(o)]))
+        assert all(p.wait() == 0 for p in procs), name
+        subprocess.run([nvcc, "-shared", "-o", str(VAR / f"libqtrack_{name}.so"), *objs, "-gencode",
+                        "arch=compute_100a,code=sm_100a"], check=True)
+        for o in objs:
+            os.unlink(o)
+        tmp.rmdir()
+        print("built", name, flags, flush=True)
+
+
+def run(E):
+    libs = [None] + sorted(VAR.glob("libqtrack_*.so"))
+    for lib in libs:
+        env = dict(os.environ)
+        if lib is not None:
+            env["QTRACK_LIB"] = str(lib)
+        r = subprocess.run([sys.executable, __file__, "one", str(E)], env=env, capture_output=True, text=True)
+        print(f"{'default' if lib is None else lib.stem[10:]:24s} {r.stdout.strip() or r.stderr[-400:]}", flush=True)
+
+
+def one(E):
+    import torch
+
+    from lqr_quadcopter_test_b200 import EnvConfig, RiccatiLQRController, SuccessCriteria, _lib, rollout_device
+
+    ctx = _lib.get_context()
+    seeds = torch.arange(E, dtype=torch.int64, device=ctx.device) + 42
+    res = []
+    for motion, cfg in (("linear", {}), ("circular", {"use_lqi": True, "q_int": [0.01, 0.01, 0.1]})):
+        env = EnvConfig()
+        env.target.motion_type = motion
+        ctrl = RiccatiLQRController(config=cfg)
+        for _ in range(3):
+            rollout_device(ctrl, env, SuccessCriteria(), seeds)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            r = rollout_device(ctrl, env, SuccessCriteria(), seeds)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        steps = float(r["metrics"][0].sum().item())
+        import numpy as np
+        res.append(f"{motion}{'_lqi' if cfg else ''}: {steps / ms * 1e3:.4e} steps/s ({ms:.1f} ms, nnz(K)={int(np.count_nonzero(ctrl.effective_gain()))})")
+    print("   ".join(res))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build(sys.argv[2:])
+    elif sys.argv[1] == "run":
+        run(int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20)
+    else:
+        one(int(sys.argv[2]))
