@@ -12,7 +12,8 @@ scaling: every rank gets its own 2^20 episodes (seeds disjoint).  Prints ONE JSO
   value      env-steps/s over all ranks, initial conditions already resident in HBM
   e2e        the same pass through the host-buffer C-ABI call (qt_evaluate_host): pinned host seeds
              in, H2D, reset kernel, rollout kernel, D2H of the [16, E] metric array out
-  roofline   rollout kernel vs the FP64 pipe: 440 algorithmic flops per env step
+  roofline   rollout kernel vs the FP64 pipe: algorithmic flops per env step of the path that ran (440
+             dense; 324 when the gain is axis-decoupled and yaw is zero, see below)
              over the kernel's CUDA-event duration, against a DFMA peak probed in this same run
              (MEASURED_PEAKS.json has no FP64 figure); HBM numbers are given for context
   cpu_baseline  the CPU oracle (C restatement of the reference's loop, all host threads) on a bounded
@@ -38,7 +39,14 @@ if str(ROOT) not in sys.path:
 
 EPISODES_PER_GPU = 1 << 20
 STEPS_PER_EPISODE = 3000
-FLOPS_PER_ENV_STEP = 440.0           # LQR, linear target, RK4
+FLOPS_PER_ENV_STEP = 440.0           # LQR, linear target, RK4, dense 4x6 gain, 3 angles
+# The reference's designs command zero yaw rate through an axis-decoupled gain (6 non-zeros of 24) and
+# start at zero yaw; qt_rollout then runs its structure-exploiting loop, which skips the products with
+# exact zeros and the identically-zero yaw chain.  Work that path still has to do, itemised like
+# mat-vec 44 -> 9, thrust direction 4 x (12 -> 3), rate loop 4 x (12 -> 8), stage
+# combinations 156 -> 130 (10 of 12 states), constraints 26 -> 23:  440 - 35 - 36 - 16 - 26 - 3 = 324
+# (and 16 instead of 24 sin/cos).  The roofline is quoted on the flops of the path that ran.
+FLOPS_PER_ENV_STEP_STRUCTURED = 324.0
 DARE_BATCH = 65536
 DARE_N = 6
 METRIC = "closed-loop env-steps/s (Riccati-LQR, linear target, 30 s episodes at dt=0.01)"
@@ -278,7 +286,13 @@ def run_gpu_arm(args) -> None:
     fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
     k_ms = statistics.mean(kernel_ms)
     steps_per_launch = steps_per_pass
-    achieved = steps_per_launch * FLOPS_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
+    Kh = np.asarray(ctrl.K)
+    pattern = np.zeros((4, 6), dtype=bool)
+    pattern[0, [2, 5]] = pattern[1, [1, 4]] = pattern[2, [0, 3]] = True
+    structured = bool(np.all(Kh[~pattern] == 0.0))   # the kernel's own test (gain_is_axis_decoupled); yaw0 = 0 after reset
+    flops_step = FLOPS_PER_ENV_STEP_STRUCTURED if structured else FLOPS_PER_ENV_STEP
+    achieved = steps_per_launch * flops_step / (k_ms * 1e-3) / 1e12
+    dense_equiv = steps_per_launch * FLOPS_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
@@ -293,10 +307,16 @@ def run_gpu_arm(args) -> None:
     except (OSError, KeyError, ValueError):
         pass
     roofline = {
-        "bound": "fp64", "kernel": "rollout_kernel<linear, LQR, lean>", "achieved": achieved, "peak": fp64_tflops,
+        "bound": "fp64", "kernel": "rollout_kernel<linear, LQR, lean>" + (" structured loop" if structured else " general loop"),
+        "achieved": achieved, "peak": fp64_tflops,
         "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops > 0 else None, "traffic": traffic,
         "peak_source": "register-resident DFMA probe (qt_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
-        "algorithmic_flops_per_env_step": FLOPS_PER_ENV_STEP, "kernel_ms": k_ms,
+        "algorithmic_flops_per_env_step": flops_step, "dense_flops_per_env_step": FLOPS_PER_ENV_STEP,
+        "dense_equivalent_tflops": dense_equiv,
+        "note": "achieved counts only the flops the executed path needs (324 of the dense 440: products with the "
+                "gain's exact zeros and the identically-zero yaw chain are skipped, bit-identically); "
+                "dense_equivalent_tflops = env-steps/s x 440 is given for comparison with earlier rounds",
+        "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms * args.steps / elapsed_ms if world == 1 else None,
         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (k_ms * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

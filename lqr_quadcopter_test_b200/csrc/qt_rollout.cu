@@ -253,10 +253,15 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             err_pre = err_post;
         }
         };
+#ifdef QT_EXPERIMENT_FAST_ONLY   // A/B experiment: register budget of the structured loop on its own
+        (void)warp_fast;
+        step_loop(std::true_type{});
+#else
         if (warp_fast)
             step_loop(std::true_type{});
         else
             step_loop(std::false_type{});
+#endif
         double ov_max = cold[CR_OV_MAX * T];
         if (in_phase && streak >= P.overshoot_window) {
             ov_count += 1;

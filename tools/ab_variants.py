@@ -66,16 +66,18 @@ def one(E):
         for _ in range(3):
             rollout_device(ctrl, env, SuccessCriteria(), seeds)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
+        evs[0].record()
+        for i in range(8):
             r = rollout_device(ctrl, env, SuccessCriteria(), seeds)
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(8)]
+        ms = sorted(per)[len(per) // 2]
+        spread = f"{min(per):.1f}-{max(per):.1f}"
         steps = float(r["metrics"][0].sum().item())
         import numpy as np
-        res.append(f"{motion}{'_lqi' if cfg else ''}: {steps / ms * 1e3:.4e} steps/s ({ms:.1f} ms, nnz(K)={int(np.count_nonzero(ctrl.effective_gain()))})")
+        res.append(f"{motion}{'_lqi' if cfg else ''}: {steps / ms * 1e3:.4e} steps/s (median {ms:.1f} ms of {spread}, nnz(K)={int(np.count_nonzero(ctrl.effective_gain()))})")
     print("   ".join(res))
 
 
