@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QT_ABI_VERSION 2
+#define QT_ABI_VERSION 3
 
 #define QT_STATE_DIM 12     /* env/quadcopter_env.py:63-70  [p(3) v(3) roll,pitch,yaw  p,q,r] */
 #define QT_ACTION_DIM 4     /* thrust, roll_rate, pitch_rate, yaw_rate (controllers/base.py:28) */
@@ -279,6 +279,46 @@ int qt_reduce_summary(qt_context *ctx, const double *metrics_dev, int64_t E, dou
 int qt_evaluate_host(qt_context *ctx, const qt_params *params, const uint64_t *seeds_host,
                      int64_t E, int64_t max_steps, int64_t chain, const double *K_host,
                      int32_t k_cols, double *metrics_host);
+
+/* ---- the deep tracking policy in the loop ------------------------------------
+ * controllers/deep_tracking_policy.py:24-147 (PolicyNetwork): 18 features -> hidden layers with one
+ * activation -> 4 outputs, action_i = sigmoid(raw_i) * (high_i - low_i) + low_i, all in fp32; the
+ * features are the fp32 cast of [p_t - p_q, v_t - v_q, attitude, body rates, p_t, v_t]
+ * (deep_tracking_policy.py:241-286).
+ * Packed weights (fp32, device): for each linear layer l = 0..n_layers-1 the TRANSPOSED weight
+ * Wt[rows_l][pad4(dims[l+1])] followed by bias[pad4(dims[l+1])], where pad4 rounds up to a multiple
+ * of 4, rows_0 = dims[0] and rows_l = pad4(dims[l]) for l > 0; padding entries are zero (an
+ * activation of 0 is 0 for all four activation kinds, so padded units are inert).
+ * qt_mlp_packed_floats() returns the buffer length.  weights_dev must be 16-byte aligned.      */
+#define QT_MLP_MAX_LAYERS 6
+#define QT_MLP_MAX_WIDTH 256
+enum qt_activation { QT_ACT_RELU = 0, QT_ACT_TANH = 1, QT_ACT_ELU = 2, QT_ACT_LEAKY_RELU = 3 };
+typedef struct qt_mlp {
+    int32_t n_layers;                    /* linear layers = hidden layers + 1                  */
+    int32_t dims[QT_MLP_MAX_LAYERS + 1]; /* dims[0] = 18, ..., dims[n_layers] = 4              */
+    int32_t activation;                  /* enum qt_activation (leaky_relu slope 0.1)          */
+    int32_t reserved;
+    float out_lo[4], out_scale[4];       /* low_i and (high_i - low_i), cast to fp32           */
+    const float *weights_dev;
+} qt_mlp;
+int64_t qt_mlp_packed_floats(const qt_mlp *policy);
+
+/* DeepTrackingPolicy.compute_action for a batch: obs [22][E] (fp64) -> action_out [4][E] (the fp32
+ * network outputs widened to fp64, as `float(action_array[i])` does).                           */
+int qt_policy_action_batched(qt_context *ctx, const qt_mlp *policy, int64_t E, const double *obs_dev,
+                             double *action_out_dev);
+
+/* The fused loop with the policy network as the acting controller (eval.py:119-165 with
+ * --controller deep; train.py:654-735 when a supervisor is given).  Same outputs as qt_rollout.
+ * If teacher_K_dev is not NULL, the control law selected by params (Riccati-LQR / LQI / PID, reset
+ * before every episode as train.py:665-667 does) is evaluated on the states the policy visits, and
+ * act_out receives ITS actions (the imitation labels); otherwise act_out receives the policy's.  */
+int qt_rollout_policy(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
+                      const double *state0_dev, const double *tparams_dev, const qt_mlp *policy,
+                      const double *teacher_K_dev, int32_t k_cols, int64_t k_stride,
+                      double *metrics_out_dev, double *final_state_out_dev, double *traj_out_dev,
+                      int64_t traj_stride, int64_t traj_slots, float *feat_out_dev, float *act_out_dev,
+                      int64_t data_stride, int64_t data_slots);
 
 /* ---- measurement helper: register-resident DFMA loop, reports the achieved FP64 rate --------
  * Used as the FP64 roofline denominator by bench.py (MEASURED_PEAKS.json has no FP64 entry). */

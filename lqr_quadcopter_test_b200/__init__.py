@@ -13,6 +13,7 @@ from .controller import (ACTION_KEYS, BaseController, LQRController, PIDControll
                          build_augmented_lqi_system, build_linearized_system, heuristic_lqr_gain,
                          solve_dare, solve_dare_batched)
 from .env import BatchedQuadcopterEnv, QuadcopterEnv
+from .policy import DeepTrackingPolicy, create_controller_from_config, make_policy_network
 from .eval import Evaluator, load_controller, rollout_device
 from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, format_metrics_report)
 from .tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
@@ -23,7 +24,8 @@ __version__ = "0.1.0"
 __all__ = [
     "EnvConfig", "QuadcopterParams", "SimulationParams", "TargetParams", "LoggingParams",
     "EnvSuccessCriteria", "SuccessCriteria", "QuadcopterEnv", "BatchedQuadcopterEnv",
-    "RiccatiLQRController", "LQRController", "PIDController", "BaseController", "ACTION_KEYS", "solve_dare",
+    "RiccatiLQRController", "LQRController", "PIDController", "DeepTrackingPolicy",
+    "create_controller_from_config", "make_policy_network", "BaseController", "ACTION_KEYS", "solve_dare",
     "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
     "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
     "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",

@@ -11,7 +11,7 @@ import os
 import pathlib
 import threading
 
-from .params import QtParams
+from .params import QtMlp, QtParams
 
 _PKG = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get("QTRACK_LIB", _PKG / "libqtrack.so"))
@@ -23,6 +23,7 @@ ABI_SYMBOLS = (
     "qt_reset_batched", "qt_rng_probe", "qt_observe_batched", "qt_compute_action_batched",
     "qt_step_batched", "qt_rollout", "qt_dare_batched", "qt_build_lqr_systems",
     "qt_reduce_scores", "qt_reduce_summary", "qt_evaluate_host", "qt_fp64_peak_probe",
+    "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy",
 )
 
 _lib = None
@@ -73,6 +74,10 @@ def load_library() -> C.CDLL:
             "qt_reduce_summary": (C.c_int, [vp, vp, i64, vp]),
             "qt_evaluate_host": (C.c_int, [vp, PP, vp, i64, i64, i64, vp, i32, vp]),
             "qt_fp64_peak_probe": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]),
+            "qt_mlp_packed_floats": (i64, [C.POINTER(QtMlp)]),
+            "qt_policy_action_batched": (C.c_int, [vp, C.POINTER(QtMlp), i64, vp, vp]),
+            "qt_rollout_policy": (C.c_int, [vp, PP, i64, i64, vp, vp, C.POINTER(QtMlp), vp, i32, i64, vp, vp, vp,
+                                            i64, i64, vp, vp, i64, i64]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(lib, name)
@@ -207,6 +212,17 @@ class Context:
         self.check(self.lib.qt_evaluate_host(
             self.handle, C.byref(params), _ptr(seeds_host), seeds_host.numel(), max_steps, chain,
             _ptr(K_host), k_cols, _ptr(metrics_host)))
+
+    def policy_action_batched(self, mlp, E, obs, action_out):
+        self.check(self.lib.qt_policy_action_batched(self.handle, C.byref(mlp), E, _ptr(obs), _ptr(action_out)))
+
+    def rollout_policy(self, params, E, max_steps, state0, tparams, mlp, teacher_K, k_cols, k_stride, metrics_out,
+                       final_state_out=None, traj_out=None, traj_stride=1, traj_slots=0, feat_out=None,
+                       act_out=None, data_stride=1, data_slots=0):
+        self.check(self.lib.qt_rollout_policy(
+            self.handle, C.byref(params), E, max_steps, _ptr(state0), _ptr(tparams), C.byref(mlp),
+            _ptr(teacher_K), k_cols, k_stride, _ptr(metrics_out), _ptr(final_state_out), _ptr(traj_out),
+            traj_stride, traj_slots, _ptr(feat_out), _ptr(act_out), data_stride, data_slots))
 
     def fp64_peak_probe(self, iters: int = 1 << 16) -> tuple[float, float]:
         tf, ms = C.c_double(), C.c_double()

@@ -17,7 +17,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libqtrack.so"
-SOURCES = ["qt_api.cu", "qt_env.cu", "qt_rollout.cu", "qt_dare.cu", "qt_reduce.cu"]
+SOURCES = ["qt_api.cu", "qt_env.cu", "qt_rollout.cu", "qt_dare.cu", "qt_reduce.cu", "qt_policy.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

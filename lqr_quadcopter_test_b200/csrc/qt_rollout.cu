@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 prev_on = on;
             }
 
-            bool log_traj = false;
+            [[maybe_unused]] bool log_traj = false;
             if constexpr (FULL) {
                 if (A.traj && step == next_traj && traj_slot < A.traj_slots) {
                     log_traj = true;

@@ -16,8 +16,12 @@ from .metrics import SuccessCriteria
 
 def teacher_dataset(controller, env_config: EnvConfig | None = None, num_episodes: int = 1024,
                     base_seed: int = 42, stride: int = 10, max_steps: int | None = None,
-                    reset_controller_between_episodes: bool = True, flatten: bool = True):
+                    reset_controller_between_episodes: bool = True, flatten: bool = True, student=None):
     """Roll out ``controller`` and return ``(features, actions, metrics)`` as CUDA tensors.
+
+    With ``student`` (a ``DeepTrackingPolicy``) the student's network drives the environment and
+    ``controller`` only labels the states it visits - the data-collection pass of the reference's
+    imitation trainer (train.py:654-735), where ``actions`` are the supervisor's.
 
     features float32 [N, 18], actions float32 [N, 4] with N = slots * num_episodes, row
     ``slot * num_episodes + episode`` (``flatten=False`` keeps [slots, E, .]); metrics float64
@@ -27,9 +31,13 @@ def teacher_dataset(controller, env_config: EnvConfig | None = None, num_episode
     env_config = env_config or EnvConfig()
     ctx = _lib.get_context()
     seeds = torch.arange(num_episodes, dtype=torch.int64, device=ctx.device) + int(base_seed)
-    chain = 1 if (reset_controller_between_episodes or not controller.carries_state()) else max(num_episodes, 2)
-    out = rollout_device(controller, env_config, SuccessCriteria(), seeds, max_steps, chain=chain,
-                         dataset_stride=stride, ctx=ctx)
+    if student is not None:
+        out = rollout_device(student, env_config, SuccessCriteria(), seeds, max_steps, dataset_stride=stride,
+                             ctx=ctx, supervisor=controller)
+    else:
+        chain = 1 if (reset_controller_between_episodes or not controller.carries_state()) else max(num_episodes, 2)
+        out = rollout_device(controller, env_config, SuccessCriteria(), seeds, max_steps, chain=chain,
+                             dataset_stride=stride, ctx=ctx)
     feats, acts = out["features"], out["actions"]
     if flatten:
         feats = feats.reshape(-1, feats.shape[-1])

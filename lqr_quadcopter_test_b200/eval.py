@@ -33,13 +33,17 @@ VALID_CONTROLLER_TYPES = ("deep", "lqr", "pid", "riccati_lqr", "lqi")  # control
 
 def rollout_device(controller, env_config: EnvConfig, criteria, seeds, max_steps: int | None = None,
                    chain: int = 1, K=None, k_stride: int | None = None, record_stride: int = 0,
-                   dataset_stride: int = 0, ctrl_state=None, want_final_state: bool = False, ctx=None):
+                   dataset_stride: int = 0, ctrl_state=None, want_final_state: bool = False, ctx=None,
+                   supervisor=None):
     """Reset + closed-loop rollout for ``seeds`` (CUDA int64 tensor [E]) entirely on the device.
 
     Returns a dict of CUDA tensors: ``metrics`` [16, E], optionally ``final_state`` [12, E],
     ``traj`` [slots, 24, E] (every ``record_stride``-th step), ``features`` float32 [slots, E, 18] and
     ``actions`` float32 [slots, E, 4] (every ``dataset_stride``-th step), ``state0``, ``tparams``.
     ``K`` overrides the controller's own gain ([groups, 4, k_cols], group = episode // k_stride).
+    A ``DeepTrackingPolicy`` controller acts through its network (``qt_rollout_policy``); with a
+    ``supervisor`` (PID / LQR / Riccati controller object, reset before every episode as train.py:665-667
+    does) ``actions`` holds the supervisor's labels for the states the policy visits.
     """
     import torch
 
@@ -47,13 +51,18 @@ def rollout_device(controller, env_config: EnvConfig, criteria, seeds, max_steps
     ctx.bind_torch_stream()
     dev = ctx.device
     E = int(seeds.numel())
-    prm = controller.kernel_params(env_config, criteria)
-    k_cols = controller.k_cols()
-    if K is None:
-        K = torch.as_tensor(np.ascontiguousarray(controller.effective_gain()), dtype=torch.float64, device=dev)
-        k_stride = E
-    elif k_stride is None:
-        k_stride = 1
+    is_policy = getattr(controller, "name", "") == "deep_tracking"
+    law = supervisor if is_policy else controller
+    if law is not None:
+        prm = law.kernel_params(env_config, criteria)
+        k_cols = law.k_cols()
+        if K is None:
+            K = torch.as_tensor(np.ascontiguousarray(law.effective_gain()), dtype=torch.float64, device=dev)
+            k_stride = E
+        elif k_stride is None:
+            k_stride = 1
+    else:
+        prm, k_cols, K, k_stride = controller.kernel_params(env_config, criteria), 6, None, E
     if max_steps is None:
         # the env ends the episode itself; this is only a safety cap on the loop length
         max_steps = int(np.ceil(env_config.simulation.max_episode_time / env_config.simulation.dt)) + 2
@@ -72,6 +81,12 @@ def rollout_device(controller, env_config: EnvConfig, criteria, seeds, max_steps
         data_slots = (max_steps + dataset_stride - 1) // dataset_stride
         out["features"] = torch.zeros((data_slots, E, P.FEATURE_DIM), dtype=torch.float32, device=dev)
         out["actions"] = torch.zeros((data_slots, E, P.ACTION_DIM), dtype=torch.float32, device=dev)
+    if is_policy:
+        ctx.rollout_policy(prm, E, max_steps, state0, tparams, controller.packed_mlp(),
+                           K.contiguous() if K is not None else None, k_cols, k_stride, out["metrics"],
+                           out.get("final_state"), out.get("traj"), max(record_stride, 1), traj_slots,
+                           out.get("features"), out.get("actions"), max(dataset_stride, 1), data_slots)
+        return out
     ctx.rollout(prm, E, max_steps, chain, state0, tparams, K.contiguous(), k_cols, k_stride, out["metrics"],
                 ctrl_state, out.get("final_state"), out.get("traj"), max(record_stride, 1), traj_slots,
                 out.get("features"), out.get("actions"), max(dataset_stride, 1), data_slots)
@@ -284,7 +299,11 @@ def load_controller(controller_type: str, checkpoint_path: str | Path | None = N
         return LQRController(config=config)
     if controller_type == "pid":
         return PIDController(config=config)
-    if controller_type in ("deep",):
-        raise NotImplementedError(
-            f"controller type '{controller_type}' is outside the accelerated Riccati-LQR/LQI path (DESIGN.md, scope)")
+    if controller_type == "deep":
+        from .policy import DeepTrackingPolicy
+
+        controller = DeepTrackingPolicy(config=config)
+        if checkpoint_path:
+            controller.load_checkpoint(checkpoint_path)
+        return controller
     raise ValueError(f"Unknown controller type: {controller_type}")

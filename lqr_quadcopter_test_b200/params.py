@@ -53,6 +53,21 @@ class QtParams(C.Structure):
         return out
 
 
+MLP_MAX_LAYERS = 6
+MLP_MAX_WIDTH = 256
+ACTIVATIONS = {"relu": 0, "tanh": 1, "elu": 2, "leaky_relu": 3}
+
+
+class QtMlp(C.Structure):
+    """Mirror of ``struct qt_mlp`` (include/qtrack.h)."""
+
+    _fields_ = [
+        ("n_layers", C.c_int32), ("dims", C.c_int32 * (MLP_MAX_LAYERS + 1)), ("activation", C.c_int32),
+        ("reserved", C.c_int32), ("out_lo", C.c_float * 4), ("out_scale", C.c_float * 4),
+        ("weights_dev", C.c_void_p),
+    ]
+
+
 def default_params() -> QtParams:
     """Reference defaults; identical to qt_params_default() in the library (checked in tests)."""
     return make_params(EnvConfig())

@@ -235,3 +235,68 @@ def solve_dare_reference(A, B, Q, R):
     BtP = B.T @ P
     K = np.linalg.solve(R + BtP @ B, BtP @ A)
     return P, K
+
+
+# ---- §8(f).2: deep tracking policy ------------------------------------------------------------------
+class _QtoMlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * 7), ("activation", C.c_int32), ("reserved", C.c_int32),
+                ("out_lo", C.c_float * 4), ("out_scale", C.c_float * 4), ("W", C.c_void_p * 6), ("b", C.c_void_p * 6)]
+
+
+class Mlp:
+    """PolicyNetwork parameters in torch's layout: weights[l] [out, in], biases[l] [out], float32."""
+
+    ACT = {"relu": 0, "tanh": 1, "elu": 2, "leaky_relu": 3}
+
+    def __init__(self, weights, biases, activation="relu", bounds=((0.0, 20.0), (-3.0, 3.0), (-3.0, 3.0), (-3.0, 3.0))):
+        self.weights = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        self.biases = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        m = _QtoMlp()
+        m.n_layers = len(self.weights)
+        m.dims[0] = self.weights[0].shape[1]
+        for l, w in enumerate(self.weights):
+            m.dims[l + 1] = w.shape[0]
+            m.W[l] = w.ctypes.data
+            m.b[l] = self.biases[l].ctypes.data
+        m.activation = self.ACT[activation]
+        for i, (lo, hi) in enumerate(bounds):
+            m.out_lo[i] = lo
+            m.out_scale[i] = hi - lo
+        self.c = m
+
+
+def policy_action(mlp: Mlp, obs):
+    obs = _f64(obs)
+    E = obs.shape[1]
+    act = np.zeros((4, E))
+    lib().qto_policy_action_batched(C.byref(mlp.c), C.c_int64(E), _p(obs), _p(act))
+    return act
+
+
+def rollout_policy(params: QtParams, state0, tparams, mlp: Mlp, K=None, k_stride=None, max_steps=3000,
+                   want_final_state=True, traj_stride=0, data_stride=0, n_threads=1):
+    """Same contract as qt_rollout_policy (include/qtrack.h)."""
+    state0, tparams = _f64(state0), _f64(tparams)
+    E = state0.shape[1]
+    k_cols = k_cols_of(params)
+    if K is not None:
+        K = _f64(K).reshape(-1, 4, k_cols)
+        if k_stride is None:
+            k_stride = E if K.shape[0] == 1 else 1
+    out = {"metrics": np.zeros((16, E))}
+    if want_final_state:
+        out["final_state"] = np.zeros((12, E))
+    traj_slots = data_slots = 0
+    if traj_stride > 0:
+        traj_slots = (max_steps + traj_stride - 1) // traj_stride
+        out["traj"] = np.zeros((traj_slots, 24, E))
+    if data_stride > 0:
+        data_slots = (max_steps + data_stride - 1) // data_stride
+        out["features"] = np.zeros((data_slots, E, 18), dtype=np.float32)
+        out["actions"] = np.zeros((data_slots, E, 4), dtype=np.float32)
+    lib().qto_rollout_policy(C.byref(params), C.c_int64(E), C.c_int64(max_steps), _p(state0), _p(tparams),
+                             C.byref(mlp.c), _p(K), C.c_int32(k_cols), C.c_int64(k_stride or E), _p(out["metrics"]),
+                             _p(out.get("final_state")), _p(out.get("traj")), C.c_int64(max(traj_stride, 1)),
+                             C.c_int64(traj_slots), _p(out.get("features")), _p(out.get("actions")),
+                             C.c_int64(max(data_stride, 1)), C.c_int64(data_slots), C.c_int32(n_threads))
+    return out

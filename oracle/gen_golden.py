@@ -557,11 +557,129 @@ def gen_pid_lqr():
     np.savez_compressed(OUT / "pid_lqr.npz", **out)
 
 
+POLICIES = {
+    # name: (hidden_sizes, activation, trained by imitation?, output bounds or None)
+    "relu_64_64": ([64, 64], "relu", True, None),
+    "tanh_32": ([32], "tanh", True, None),
+    "elu_48_40": ([48, 40], "elu", False, None),
+    "leaky_20_20_20": ([20, 20, 20], "leaky_relu", False,
+                       {"thrust": (2.0, 18.0), "roll_rate": (-2.0, 2.0), "pitch_rate": (-2.5, 2.5), "yaw_rate": (-1.0, 1.0)}),
+}
+
+
+def gen_policy():
+    """§8(f).2: the reference's DeepTrackingPolicy (torch, CPU) on fixed weights -> policy.npz.
+    Two of the networks are first fitted to the Riccati-LQR law (so the closed loop tracks and is
+    contractive); the fit itself is not part of the fixture, only the resulting weights are."""
+    import torch
+
+    from quadcopter_tracking.controllers import RiccatiLQRController
+    from quadcopter_tracking.controllers.deep_tracking_policy import DeepTrackingPolicy
+    from quadcopter_tracking.env import EnvConfig, QuadcopterEnv
+    from quadcopter_tracking.utils.metrics import SuccessCriteria
+
+    torch.set_num_threads(1)
+    out = {}
+    teacher = RiccatiLQRController(config={})
+    K = teacher.K
+    rng = np.random.default_rng(5)
+
+    def lqr_labels(feat):
+        u = feat[:, 0:6] @ K.T
+        return np.stack([np.clip(9.81 + u[:, 0], 0, 20), np.clip(u[:, 1], -3, 3), np.clip(u[:, 2], -3, 3),
+                         np.clip(u[:, 3], -3, 3)], axis=1)
+
+    def sample_features(n):
+        f = rng.standard_normal((n, 18)) * np.array([1.0] * 3 + [1.5] * 3 + [0.2] * 3 + [0.5] * 3 + [3.0] * 3 + [1.0] * 3)
+        return f
+
+    for name, (hidden, act, trained, bounds) in POLICIES.items():
+        torch.manual_seed(hash(name) % 1000 if False else len(name) * 7 + 1)
+        cfg = {"hidden_sizes": hidden, "activation": act}
+        if bounds:
+            cfg["output_bounds"] = bounds
+        pol = DeepTrackingPolicy(config=cfg, device="cpu")
+        if trained:
+            opt = torch.optim.Adam(pol.network.parameters(), lr=2e-3)
+            pol.network.train()
+            for it in range(4000):
+                f = sample_features(512)
+                x = torch.tensor(f, dtype=torch.float32)
+                y = torch.tensor(lqr_labels(f), dtype=torch.float32)
+                loss = ((pol.network(x) - y) ** 2 * torch.tensor([1.0, 30.0, 30.0, 1.0])).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            pol.network.eval()
+            print(f"  policy {name}: imitation fit loss {float(loss):.3e}", flush=True)
+        lin = [m for m in pol.network.modules() if isinstance(m, torch.nn.Linear)]
+        for l, m in enumerate(lin):
+            out[f"{name}_W{l}"] = m.weight.detach().numpy().copy()
+            out[f"{name}_b{l}"] = m.bias.detach().numpy().copy()
+        # compute_action on hand-made observations
+        obs_rows, act_rows = [], []
+        for k in range(64):
+            v = rng.standard_normal(22) * np.array([2] * 3 + [3] * 3 + [0.3] * 6 + [2] * 3 + [3] * 3 + [4] * 3 + [1])
+            if k % 9 == 0:
+                v *= 25.0          # saturates the sigmoid
+            o = {"quadcopter": {"position": v[0:3], "velocity": v[3:6], "attitude": v[6:9], "angular_velocity": v[9:12]},
+                 "target": {"position": v[12:15], "velocity": v[15:18], "acceleration": v[18:21]}, "time": float(v[21])}
+            a = pol.compute_action(o)
+            obs_rows.append(v)
+            act_rows.append([a["thrust"], a["roll_rate"], a["pitch_rate"], a["yaw_rate"]])
+        out[f"{name}_obs"], out[f"{name}_act"] = np.array(obs_rows).T, np.array(act_rows).T
+        # closed loop through the reference's driver loop
+        for motion, seeds, max_steps in (("stationary", [42, 43, 44], None if trained else 300),
+                                         ("linear", [42, 43], 1200 if trained else 300)):
+            cfg_env = EnvConfig()
+            cfg_env.target.motion_type = motion
+            recs = [run_reference_episode(cfg_env, pol, sd, SuccessCriteria(), max_steps, True) for sd in seeds]
+            key = f"{name}_{motion}"
+            out[f"{key}_seeds"] = np.array(seeds, dtype=np.uint64)
+            out[f"{key}_max_steps"] = np.array(3002 if max_steps is None else max_steps)
+            for fld in ("state0", "tparams", "metrics", "final_state"):
+                out[f"{key}_{fld}"] = np.array([r[fld] for r in recs]).T
+            out[f"{key}_samples"] = np.array([r["samples"] for r in recs])
+            print("  policy rollout", key, "steps", [int(r["metrics"][0]) for r in recs], flush=True)
+    # supervisor labels on the states the student visits (train.py:654-735), every 10th step
+    name = "relu_64_64"
+    pol = DeepTrackingPolicy(config={"hidden_sizes": [64, 64], "activation": "relu"}, device="cpu")
+    lin = [m for m in pol.network.modules() if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for l, m in enumerate(lin):
+            m.weight.copy_(torch.tensor(out[f"{name}_W{l}"]))
+            m.bias.copy_(torch.tensor(out[f"{name}_b{l}"]))
+    from quadcopter_tracking.controllers import PIDController
+    for sup_name, sup in (("riccati", RiccatiLQRController(config={})),
+                          ("pid", PIDController(config={"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4}))):
+        cfg_env = EnvConfig()
+        cfg_env.target.motion_type = "linear"
+        env = QuadcopterEnv(config=cfg_env)
+        feats, labs = [], []
+        for sd in (42, 43):
+            obs = env.reset(seed=sd)
+            sup.reset()
+            f_ep, l_ep = [], []
+            for step in range(400):
+                a_sup = sup.compute_action(obs)
+                if step % 10 == 0:
+                    f_ep.append(pol._extract_features(obs))
+                    l_ep.append(np.array([a_sup["thrust"], a_sup["roll_rate"], a_sup["pitch_rate"], a_sup["yaw_rate"]],
+                                         dtype=np.float32))
+                obs, _, done, _ = env.step(pol.compute_action(obs))
+                if done:
+                    break
+            feats.append(f_ep), labs.append(l_ep)
+        out[f"dagger_{sup_name}_features"] = np.array(feats).transpose(1, 0, 2)   # [slots, E, 18]
+        out[f"dagger_{sup_name}_labels"] = np.array(labs).transpose(1, 0, 2)      # [slots, E, 4]
+    np.savez_compressed(OUT / "policy.npz", **out)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     _import_reference()
     cwd = os.getcwd()
-    every = (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts, gen_pid_lqr)
+    every = (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts, gen_pid_lqr, gen_policy)
     chosen = [fn for fn in every if fn.__name__ in sys.argv[1:]] or every   # e.g. `gen_golden.py gen_pid_lqr`
     for fn in chosen:
         print(fn.__name__, flush=True)

@@ -132,3 +132,38 @@ def pid_lqr_case(name: str):
     env = EnvConfig()
     env.target.motion_type = name.split("_")[-1]
     return P.make_params(env, controller_ns(**kw), SuccessCriteria()), max_steps, chain, TOL_LQR, cfg, env
+
+
+# ---- §8(f).2: deep tracking policy fixtures (tests/golden/policy.npz) --------------------------------
+# fp32 network: torch (the reference), the C oracle and the CUDA kernel accumulate the dot products in
+# different orders (and the kernel contracts into FMA), so single actions agree to a few fp32 ulps of
+# the 20 N thrust range and 30 s closed loops to ~1e-5; stated tolerances carry a 10x margin.
+TOL_POLICY_ACTION = 5e-5
+TOL_POLICY_STATE = 1e-4
+POLICIES = {
+    "relu_64_64": ([64, 64], "relu", None),
+    "tanh_32": ([32], "tanh", None),
+    "elu_48_40": ([48, 40], "elu", None),
+    "leaky_20_20_20": ([20, 20, 20], "leaky_relu",
+                       {"thrust": (2.0, 18.0), "roll_rate": (-2.0, 2.0), "pitch_rate": (-2.5, 2.5), "yaw_rate": (-1.0, 1.0)}),
+}
+
+
+def policy_arrays(npz, name):
+    n = len(POLICIES[name][0]) + 1
+    return [npz[f"{name}_W{l}"] for l in range(n)], [npz[f"{name}_b{l}"] for l in range(n)]
+
+
+def assert_policy_rollout_matches(np, got, npz, key):
+    M, G = got["metrics"], npz[key + "_metrics"]
+    hard = [P.M_STEPS, P.M_TERMINATION, P.M_VIOLATIONS]
+    np.testing.assert_array_equal(M[hard], G[hard], err_msg=key)
+    soft = [P.M_ENV_ON_TARGET, P.M_MET_ON_TARGET]
+    assert np.abs(M[soft] - G[soft]).max() <= 2, f"{key}: on-target counts beyond borderline flips"
+    np.testing.assert_allclose(M[SUM_ROWS], G[SUM_ROWS], rtol=2e-5, atol=1e-3, err_msg=key)
+    np.testing.assert_allclose(M[[P.M_FINAL_TIME, P.M_MAX_ERR, P.M_FINAL_ERR]], G[[P.M_FINAL_TIME, P.M_MAX_ERR, P.M_FINAL_ERR]],
+                               rtol=0, atol=TOL_POLICY_STATE, err_msg=key)
+    np.testing.assert_allclose(got["final_state"], npz[key + "_final_state"], rtol=0, atol=TOL_POLICY_STATE, err_msg=key)
+    samples = npz[key + "_samples"]
+    traj = np.transpose(got["traj"][: samples.shape[1], P.TRAJ_STATE:P.TRAJ_STATE + 12, :], (2, 0, 1))
+    np.testing.assert_allclose(traj, samples, rtol=0, atol=TOL_POLICY_STATE, err_msg=key)

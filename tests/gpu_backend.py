@@ -127,3 +127,47 @@ def dare(A, B, Q, R):
 
     P, K, iters, info = solve_dare_batched(A, B, Q, R)
     return P.cpu().numpy(), K.cpu().numpy(), iters.cpu().numpy(), info.cpu().numpy()
+
+
+# ---- §8(f).2: deep tracking policy -------------------------------------------------------------------
+def make_policy(golden_npz, name):
+    """DeepTrackingPolicy drop-in object loaded with the fixture weights."""
+    import golden_cases as gc
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy
+
+    hidden, act, bounds = gc.POLICIES[name]
+    cfg = {"hidden_sizes": hidden, "activation": act}
+    if bounds:
+        cfg["output_bounds"] = bounds
+    pol = DeepTrackingPolicy(config=cfg)
+    pol.load_arrays(*gc.policy_arrays(golden_npz, name))
+    return pol
+
+
+def policy_action(policy, obs):
+    return policy.compute_action_batched(dev(obs)).cpu().numpy()
+
+
+def rollout_policy(params, state0, tparams, policy, K=None, k_stride=None, max_steps=3000, traj_stride=0, data_stride=0):
+    c = ctx()
+    E = state0.shape[1]
+    k_cols = k_cols_of(params)
+    Kt = None
+    if K is not None:
+        Kt = dev(np.asarray(K).reshape(-1, 4, k_cols))
+        if k_stride is None:
+            k_stride = E if Kt.shape[0] == 1 else 1
+    f64 = dict(dtype=torch.float64, device=c.device)
+    out = {"metrics": torch.zeros((16, E), **f64), "final_state": torch.zeros((12, E), **f64)}
+    ts = dsl = 0
+    if traj_stride > 0:
+        ts = (max_steps + traj_stride - 1) // traj_stride
+        out["traj"] = torch.zeros((ts, 24, E), **f64)
+    if data_stride > 0:
+        dsl = (max_steps + data_stride - 1) // data_stride
+        out["features"] = torch.zeros((dsl, E, 18), dtype=torch.float32, device=c.device)
+        out["actions"] = torch.zeros((dsl, E, 4), dtype=torch.float32, device=c.device)
+    c.rollout_policy(params, E, max_steps, dev(state0), dev(tparams), policy.packed_mlp(), Kt, k_cols, k_stride or E,
+                     out["metrics"], out["final_state"], out.get("traj"), max(traj_stride, 1), ts,
+                     out.get("features"), out.get("actions"), max(data_stride, 1), dsl)
+    return {k: v.cpu().numpy() for k, v in out.items()}

@@ -323,3 +323,67 @@ def test_pid_and_lqr_tuner_matches_reference(golden, tmp_path):
                          r["metrics"]["success_rate"]] for r in res.all_results])
         np.testing.assert_allclose(met, g[f"tune_{key}_metrics"], rtol=0, atol=1e-10, err_msg=key)
         assert abs(res.best_score - float(g[f"tune_{key}_best_score"])) < 1e-10
+
+
+# ---- §8(f).2: deep tracking policy in the loop ------------------------------------------------------
+@pytest.mark.parametrize("name", list(gc.POLICIES))
+def test_policy_network_matches_reference(golden, gb, name):
+    """qt_policy_action_batched / qt_rollout_policy against torch's fp32 network driven by the
+    reference's own loop (fixture), incl. widths that need padding and custom output bounds."""
+    g = golden["policy"]
+    pol = gb.make_policy(g, name)
+    act = gb.policy_action(pol, g[name + "_obs"])
+    np.testing.assert_allclose(act, g[name + "_act"], rtol=0, atol=gc.TOL_POLICY_ACTION)
+    v = g[name + "_obs"][:, 3]
+    a = pol.compute_action({"quadcopter": {"position": v[0:3], "velocity": v[3:6], "attitude": v[6:9],
+                                           "angular_velocity": v[9:12]},
+                            "target": {"position": v[12:15], "velocity": v[15:18], "acceleration": v[18:21]},
+                            "time": float(v[21])})
+    np.testing.assert_allclose([a["thrust"], a["roll_rate"], a["pitch_rate"], a["yaw_rate"]], g[name + "_act"][:, 3],
+                               rtol=0, atol=gc.TOL_POLICY_ACTION)
+    for motion in ("stationary", "linear"):
+        key = f"{name}_{motion}"
+        env = EnvConfig()
+        env.target.motion_type = motion
+        out = gb.rollout_policy(P.make_params(env), g[key + "_state0"], g[key + "_tparams"], pol,
+                                max_steps=int(g[key + "_max_steps"]), traj_stride=250)
+        gc.assert_policy_rollout_matches(np, out, g, key)
+
+
+@pytest.mark.parametrize("sup", ["riccati", "pid"])
+def test_supervisor_labels_on_student_states_match_reference(golden, gb, sup):
+    """train.py:654-735 data collection through the public API (teacher_dataset(student=...))."""
+    from lqr_quadcopter_test_b200 import PIDController, RiccatiLQRController, teacher_dataset
+
+    g = golden["policy"]
+    pol = gb.make_policy(g, "relu_64_64")
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    teacher = (PIDController(config={"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4}) if sup == "pid"
+               else RiccatiLQRController(config={}))
+    feats, labels, _ = teacher_dataset(teacher, env, num_episodes=2, base_seed=42, stride=10, max_steps=400,
+                                       flatten=False, student=pol)
+    np.testing.assert_allclose(feats.cpu().numpy(), g[f"dagger_{sup}_features"], rtol=0, atol=gc.TOL_POLICY_STATE)
+    np.testing.assert_allclose(labels.cpu().numpy(), g[f"dagger_{sup}_labels"], rtol=0, atol=gc.TOL_POLICY_STATE)
+
+
+def test_deep_policy_evaluator_and_checkpoint_round_trip(golden, gb, tmp_path):
+    """`eval --controller deep --checkpoint ...`: save in the reference's checkpoint format, load through
+    load_controller, evaluate; per-episode metrics equal the fixture's."""
+    from lqr_quadcopter_test_b200 import EnvConfig as EC, Evaluator, SuccessCriteria, load_controller
+
+    g = golden["policy"]
+    pol = gb.make_policy(g, "relu_64_64")
+    ck = tmp_path / "policy.pt"
+    pol.save_checkpoint(ck, metadata={"epoch": 3})
+    loaded = load_controller("deep", checkpoint_path=ck, config={"hidden_sizes": [64, 64], "activation": "relu"})
+    ev = Evaluator(loaded, EC(), SuccessCriteria(), output_dir=tmp_path)
+    s = ev.evaluate(num_episodes=3, base_seed=42, verbose=False)
+    G = g["relu_64_64_stationary_metrics"]
+    ratios = np.array([m.on_target_ratio for m in s.episode_metrics])
+    assert np.abs(ratios * 3000 - G[P.M_MET_ON_TARGET]).max() <= 2
+    np.testing.assert_allclose([m.mean_tracking_error for m in s.episode_metrics], G[P.M_SUM_ERR] / G[P.M_STEPS],
+                               rtol=2e-5)
+    assert s.total_episodes == 3 and len(ev.episode_data_list[0]) == 3000
+    with pytest.raises(ValueError, match="Hidden sizes mismatch"):
+        load_controller("deep", checkpoint_path=ck, config={"hidden_sizes": [32]})

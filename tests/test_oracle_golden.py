@@ -234,3 +234,45 @@ def test_pid_and_lqr_tuner_scores_match_reference(golden):
         cand = oracle.reduce_scores(out["metrics"], C_, eps)
         np.testing.assert_allclose(cand[0], g[f"tune_{key}_score"], rtol=0, atol=1e-12, err_msg=key)
         np.testing.assert_allclose(cand[1:4].T, g[f"tune_{key}_metrics"], rtol=0, atol=1e-12, err_msg=key)
+
+
+# ---- §8(f).2: deep tracking policy -------------------------------------------------------------------
+def _oracle_mlp(g, name):
+    hidden, act, bounds = gc.POLICIES[name]
+    W, b = gc.policy_arrays(g, name)
+    kw = {} if bounds is None else {"bounds": tuple(bounds[k] for k in ("thrust", "roll_rate", "pitch_rate", "yaw_rate"))}
+    return oracle.Mlp(W, b, act, **kw)
+
+
+@pytest.mark.parametrize("name", list(gc.POLICIES))
+def test_policy_network_matches_reference(golden, name):
+    """DeepTrackingPolicy.compute_action and the closed loop under it (torch fp32 on the CPU)."""
+    g = golden["policy"]
+    m = _oracle_mlp(g, name)
+    act = oracle.policy_action(m, g[name + "_obs"])
+    np.testing.assert_allclose(act, g[name + "_act"], rtol=0, atol=gc.TOL_POLICY_ACTION)
+    for motion in ("stationary", "linear"):
+        key = f"{name}_{motion}"
+        env = EnvConfig()
+        env.target.motion_type = motion
+        out = oracle.rollout_policy(P.make_params(env), g[key + "_state0"], g[key + "_tparams"], m,
+                                    max_steps=int(g[key + "_max_steps"]), traj_stride=250)
+        gc.assert_policy_rollout_matches(np, out, g, key)
+
+
+@pytest.mark.parametrize("sup", ["riccati", "pid"])
+def test_supervisor_labels_on_student_states_match_reference(golden, sup):
+    """train.py:654-735: the student drives, the supervisor labels (every 10th step recorded)."""
+    g = golden["policy"]
+    m = _oracle_mlp(g, "relu_64_64")
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    if sup == "pid":
+        prm = P.make_params(env, gc.controller_ns(name="pid", integral_limit=0.4))
+        K = np.array([[0.01, 0.01, 4.0], [0.002, 0.002, 0.5], [0.06, 0.06, 2.0], [0.0, 0.0, 0.0]])
+    else:
+        prm, K = P.make_params(env, gc.controller_ns()), golden["dare"]["lqr_default_K"]
+    s0, tp = oracle.reset_reference(prm, [42, 43])
+    out = oracle.rollout_policy(prm, s0, tp, m, K=K, max_steps=400, data_stride=10)
+    np.testing.assert_allclose(out["features"], g[f"dagger_{sup}_features"], rtol=0, atol=gc.TOL_POLICY_STATE)
+    np.testing.assert_allclose(out["actions"], g[f"dagger_{sup}_labels"], rtol=0, atol=gc.TOL_POLICY_STATE)
