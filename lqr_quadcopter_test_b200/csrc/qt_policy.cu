@@ -215,6 +215,13 @@ __global__ void __launch_bounds__(kPolicyThreads, 2)
     while (term == QT_TERM_NONE && step < A.max_steps) {
         // ---- the policy acts on the pre-step observation
         write_features<T>(s, tp, tv, xa);
+        const bool log_data = A.feat && step == next_data && data_slot < A.data_slots;
+        if (log_data) {  // before the forward pass: the activation tiles are reused by the layers
+            float *f = A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM;
+#pragma unroll
+            for (int i = 0; i < QT_FEATURE_DIM; i += 2)
+                *reinterpret_cast<float2 *>(f + i) = make_float2(xa[i * T], xa[(i + 1) * T]);
+        }
         float out[4];
         mlp_forward<T>(M, W, xa, xb, out);
         double act[4] = {(double)out[0], (double)out[1], (double)out[2], (double)out[3]};
@@ -273,12 +280,8 @@ __global__ void __launch_bounds__(kPolicyThreads, 2)
 #pragma unroll
             for (int i = 0; i < 4; i++) row[(int64_t)(QT_TRAJ_ACTION + i) * E] = act[i];
         }
-        if (A.feat && step == next_data && data_slot < A.data_slots) {
-            float *f = A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM;
+        if (log_data) {
             float2 *y = reinterpret_cast<float2 *>(A.actf + ((int64_t)data_slot * E + e) * QT_ACTION_DIM);
-#pragma unroll
-            for (int i = 0; i < QT_FEATURE_DIM; i += 2)
-                *reinterpret_cast<float2 *>(f + i) = make_float2(xa[i * T], xa[(i + 1) * T]);
             y[0] = make_float2((float)lab[0], (float)lab[1]);
             y[1] = make_float2((float)lab[2], (float)lab[3]);
             next_data += A.data_stride;
