@@ -14,6 +14,7 @@ from .controller import (ACTION_KEYS, BaseController, LQRController, PIDControll
                          solve_dare, solve_dare_batched)
 from .env import BatchedQuadcopterEnv, QuadcopterEnv
 from .policy import DeepTrackingPolicy, create_controller_from_config, make_policy_network
+from .train import Trainer, TrainingConfig, load_checkpoint_and_resume
 from .eval import Evaluator, load_controller, rollout_device
 from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, format_metrics_report)
 from .tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
@@ -25,7 +26,8 @@ __all__ = [
     "EnvConfig", "QuadcopterParams", "SimulationParams", "TargetParams", "LoggingParams",
     "EnvSuccessCriteria", "SuccessCriteria", "QuadcopterEnv", "BatchedQuadcopterEnv",
     "RiccatiLQRController", "LQRController", "PIDController", "DeepTrackingPolicy",
-    "create_controller_from_config", "make_policy_network", "BaseController", "ACTION_KEYS", "solve_dare",
+    "create_controller_from_config", "make_policy_network", "Trainer", "TrainingConfig",
+    "load_checkpoint_and_resume", "BaseController", "ACTION_KEYS", "solve_dare",
     "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
     "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
     "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",

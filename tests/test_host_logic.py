@@ -198,3 +198,27 @@ def test_controller_configuration_errors_come_before_any_gpu_work():
         RiccatiLQRController(config={"R": np.eye(3)})
     with pytest.raises(ValueError, match=r"Q matrix must have shape \(6, 6\)"):
         RiccatiLQRController(config={"Q": np.eye(5)})
+
+
+def test_training_config_mirrors_the_reference(tmp_path):
+    """train.py:60-273: field names, defaults, validation messages, dict / file round trip."""
+    import json
+
+    from lqr_quadcopter_test_b200 import TrainingConfig
+
+    c = TrainingConfig()
+    assert (c.controller, c.epochs, c.episodes_per_epoch, c.batch_size, c.training_mode) == ("deep", 100, 10, 32, "tracking")
+    assert c.hidden_sizes == [64, 64] and c.supervisor_controller == "pid" and c.target_motion_type == "circular"
+    with pytest.raises(ValueError, match="Invalid training_mode"):
+        TrainingConfig(training_mode="dagger")
+    with pytest.raises(ValueError, match="Invalid supervisor_controller"):
+        TrainingConfig(supervisor_controller="mpc")
+    with pytest.raises(ValueError, match="Invalid controller type"):
+        TrainingConfig(controller="mpc")
+    d = {"training_mode": "imitation", "supervisor_controller": "riccati_lqr", "epochs": 3, "pid": {"kp_pos": [1, 1, 1]},
+         "not_a_field": 7}
+    path = tmp_path / "cfg.json"
+    path.write_text(json.dumps(d))
+    c2 = TrainingConfig.from_file(path)
+    assert c2.epochs == 3 and c2.full_config["pid"] == {"kp_pos": [1, 1, 1]} and "not_a_field" not in c2.to_dict()
+    assert TrainingConfig.from_dict(c2.to_dict()).to_dict() == c2.to_dict()
