@@ -213,11 +213,10 @@ class ControllerTuner:
         out = Path(os.environ.get("TUNING_OUTPUT_DIR", config.output_dir))
         _validate_path(out)
         self.output_dir = out
-        if config.strategy == "cma_es":
-            try:
-                import cma  # noqa: F401
-            except ImportError:
-                raise ImportError("CMA-ES strategy requires the 'cma' package. Install it with: pip install cma")
+        # strategy "cma_es": the reference needs the optional third-party `cma` package (tuning.py:636-643);
+        # here the ask/tell loop is cmaes.py, so the strategy is always available
+        self.cma_es = None
+        self._cma_param_spec: list[tuple[str, int, tuple]] = []
 
     # -- candidate generation: host, identical RNG consumption to tuning.py:662-735 -----------------
     def _draw(self, rng_def):
@@ -421,7 +420,8 @@ class ControllerTuner:
             configs = self._generate_grid_configs()
             configs = configs[: min(len(configs), cfg.max_iterations)]
         elif cfg.strategy == "cma_es":
-            raise NotImplementedError("CMA-ES ask/tell is host bookkeeping outside the accelerated path")
+            self._run_cma_es_search()
+            configs = []
         else:
             remaining = cfg.max_iterations - len(self.results)
             configs = [self._generate_random_config() for _ in range(max(remaining, 0))]
@@ -434,6 +434,83 @@ class ControllerTuner:
             timestamp=datetime.now(timezone.utc).isoformat(), config=cfg.to_dict())
         self._save_results(result)
         return result
+
+    # -- CMA-ES (tuning.py:1156-1428): specification, bounds, x0 and sigma0 as in the reference; ask/tell
+    # from cmaes.py; one generation = one batched evaluation ------------------------------------------------
+    def _build_cma_param_spec(self) -> list[tuple[str, int, tuple]]:
+        sp = self.config.search_space
+        spec = []
+        for name, dim in (("kp_pos", 3), ("ki_pos", 3), ("kd_pos", 3), ("ff_velocity_gain", 3),
+                          ("ff_acceleration_gain", 3), ("q_pos", 3), ("q_vel", 3), ("r_thrust", 1), ("r_rate", 1),
+                          ("r_controls", 4), ("q_int", 3)):
+            rng_def = getattr(sp, name + "_range")
+            if rng_def is not None:
+                spec.append((name, dim, rng_def))
+        return spec
+
+    def _get_cma_bounds(self) -> tuple[list[float], list[float]]:
+        lower, upper = [], []
+        for _name, dim, bounds in self._cma_param_spec:
+            if dim == 1:
+                lower.append(bounds[0])
+                upper.append(bounds[1])
+            else:
+                lower.extend(bounds[0])
+                upper.extend(bounds[1])
+        return lower, upper
+
+    def _get_cma_x0(self) -> list[float]:
+        lower, upper = self._get_cma_bounds()
+        x0, idx = [], 0
+        for name, dim, _ in self._cma_param_spec:
+            log_scale = name in {"q_pos", "q_vel", "r_controls", "q_int"}
+            for _ in range(dim):
+                lo, hi = lower[idx], upper[idx]
+                x0.append(float(np.sqrt(lo * hi)) if (log_scale and lo > 0 and hi > 0) else (lo + hi) / 2.0)
+                idx += 1
+        return x0
+
+    def _vector_to_config(self, x) -> dict:
+        cfg: dict = {}
+        idx = 0
+        for name, dim, _ in self._cma_param_spec:
+            if dim == 1:
+                cfg[name] = float(x[idx])
+                idx += 1
+            else:
+                cfg[name] = [float(x[idx + i]) for i in range(dim)]
+                idx += dim
+        if "ff_velocity_gain" in cfg or "ff_acceleration_gain" in cfg:
+            cfg["feedforward_enabled"] = True
+        if "q_int" in cfg or self.config.search_space.use_lqi:
+            cfg["use_lqi"] = True
+        return cfg
+
+    def _run_cma_es_search(self) -> None:
+        from .cmaes import CMAEvolutionStrategy
+
+        cfg = self.config
+        self._cma_param_spec = self._build_cma_param_spec()
+        if not self._cma_param_spec:
+            logger.warning("No parameters to tune. CMA-ES requires at least one range.")
+            return
+        lower, upper = self._get_cma_bounds()
+        x0 = self._get_cma_x0()
+        ranges = [hi - lo for lo, hi in zip(lower, upper) if hi > lo]
+        sigma0 = 1e-5 if not ranges else cfg.cma_sigma0 * float(np.exp(np.mean(np.log(ranges))))
+        self.cma_es = CMAEvolutionStrategy(x0, sigma0, lower, upper, seed=cfg.seed, popsize=cfg.cma_popsize,
+                                           tolfun=1e-11, tolx=1e-12, maxfevals=cfg.max_iterations)
+        num_evals = len(self.results)
+        while not self.cma_es.stop() and num_evals < cfg.max_iterations and not self.interrupted:
+            solutions = self.cma_es.ask()[: cfg.max_iterations - num_evals]
+            repaired = [self.cma_es.repair(x) for x in solutions]
+            configs = [self._vector_to_config(x) for x in repaired]
+            scores, metrics = self.evaluate_configs(configs)     # the whole generation in one launch
+            for c, s, m in zip(configs, scores, metrics):
+                self._record_result(c, s, m)
+            num_evals += len(solutions)
+            if len(solutions) >= self.cma_es.mu:
+                self.cma_es.tell(solutions, [self.cma_es.penalised(x, -s) for x, s in zip(solutions, scores)])
 
     def _save_results(self, result: TuningResult) -> None:
         """tuning.py:1103-1150: timestamped results + a stable "latest" copy."""

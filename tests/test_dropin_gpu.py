@@ -176,3 +176,31 @@ def test_teacher_dataset_shapes_and_content():
     assert bool((f0[:, 6:12] == 0).all()) and float(f0[:, 0:3].abs().max()) <= 0.5
     assert bool(((acts[:, 0] >= 0) & (acts[:, 0] <= 20)).all()) and bool((acts[:, 1:].abs() <= 3).all())
     assert bool((metrics[0] == 1000).all())
+
+
+def test_cma_es_strategy_runs_generations_as_batches_and_improves(gpu_ctx, tmp_path):
+    """§8(f).3: strategy="cma_es" (tuning.py:1313-1428) without the `cma` package: every generation is
+    one batched DARE + rollout evaluation; the search improves on its own first generation."""
+    from lqr_quadcopter_test_b200 import ControllerTuner, GainSearchSpace, TuningConfig
+
+    space = GainSearchSpace(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), q_vel_range=([1e-3, 1e-3, 2.0], [1e-2, 1e-2, 8.0]),
+                            r_controls_range=([0.5] * 4, [2.0] * 4))
+    tc = TuningConfig(controller_type="riccati_lqr", search_space=space, strategy="cma_es", max_iterations=120,
+                      evaluation_episodes=4, evaluation_horizon=600, seed=42, target_motion_type="linear",
+                      episode_length=6.0, output_dir=str(tmp_path), cma_popsize=12)
+    tuner = ControllerTuner(tc)
+    launches0 = gpu_ctx.launches
+    res = tuner.tune()
+    assert res.iterations_completed == 120 and len(res.all_results) == 120
+    # 10 generations; each is reset + build + validate + DARE + rollout + reduce, not 12 separate evaluations
+    assert gpu_ctx.launches - launches0 <= 10 * 8
+    scores = np.array([r["score"] for r in res.all_results])
+    assert res.best_score == scores.max() and scores[-24:].mean() > scores[:12].mean()
+    lo = np.array([5e-5, 5e-5, 10.0]), np.array([5e-4, 5e-4, 25.0])
+    for r in res.all_results:      # evaluated candidates are always inside the box
+        assert np.all(np.array(r["config"]["q_pos"]) >= lo[0]) and np.all(np.array(r["config"]["q_pos"]) <= lo[1])
+    pid = TuningConfig(controller_type="pid", strategy="cma_es", max_iterations=24, evaluation_episodes=2,
+                       evaluation_horizon=300, episode_length=3.0, target_motion_type="linear", output_dir=str(tmp_path / "p"),
+                       search_space=GainSearchSpace(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]),
+                                                    kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])))
+    assert ControllerTuner(pid).tune().iterations_completed == 24

@@ -119,8 +119,7 @@ def test_grid_candidates_match_the_reference(golden, tmp_path):
 
 def test_tuner_rejects_what_is_out_of_scope(tmp_path):
     ControllerTuner(TuningConfig(controller_type="pid", output_dir=str(tmp_path)))   # §8(f).1: in scope now
-    with pytest.raises(ImportError, match="cma"):
-        ControllerTuner(TuningConfig(controller_type="riccati_lqr", strategy="cma_es", output_dir=str(tmp_path)))
+    ControllerTuner(TuningConfig(controller_type="riccati_lqr", strategy="cma_es", output_dir=str(tmp_path)))   # §8(f).3
     with pytest.raises(ValueError, match="traversal"):
         ControllerTuner(TuningConfig(controller_type="riccati_lqr", output_dir="../evil"))
 
@@ -222,3 +221,30 @@ def test_training_config_mirrors_the_reference(tmp_path):
     c2 = TrainingConfig.from_file(path)
     assert c2.epochs == 3 and c2.full_config["pid"] == {"kp_pos": [1, 1, 1]} and "not_a_field" not in c2.to_dict()
     assert TrainingConfig.from_dict(c2.to_dict()).to_dict() == c2.to_dict()
+
+
+def test_cma_es_specification_and_convergence(tmp_path):
+    """tuning.py:1156-1262: parameter spec, bounds, x0 (geometric mean for Q/R weights) as in the reference;
+    the ask/tell loop (cmaes.py) converges on a bounded quadratic, including an optimum on the boundary."""
+    from lqr_quadcopter_test_b200.cmaes import CMAEvolutionStrategy
+
+    sp = GainSearchSpace(q_pos_range=([1e-4, 1e-4, 10.0], [4e-4, 9e-4, 20.0]), r_thrust_range=(0.5, 2.0),
+                         kp_pos_range=([0.0, 0.0, 2.0], [0.1, 0.1, 6.0]))
+    t = ControllerTuner(TuningConfig(controller_type="riccati_lqr", strategy="cma_es", search_space=sp, output_dir=str(tmp_path)))
+    t._cma_param_spec = t._build_cma_param_spec()
+    assert [n for n, _, _ in t._cma_param_spec] == ["kp_pos", "q_pos", "r_thrust"]
+    lo, hi = t._get_cma_bounds()
+    assert lo == [0.0, 0.0, 2.0, 1e-4, 1e-4, 10.0, 0.5] and hi == [0.1, 0.1, 6.0, 4e-4, 9e-4, 20.0, 2.0]
+    np.testing.assert_allclose(t._get_cma_x0(), [0.05, 0.05, 4.0, 2e-4, 3e-4, np.sqrt(200.0), 1.25])
+    cfg = t._vector_to_config(list(range(7)))
+    assert cfg == {"kp_pos": [0.0, 1.0, 2.0], "q_pos": [3.0, 4.0, 5.0], "r_thrust": 6.0}
+    lo, hi = np.array(lo), np.array(hi)
+    opt = lo + (hi - lo) * np.array([0.3, 0.7, 0.5, 0.2, 0.9, 0.0, 1.0])
+    f = lambda x: float(np.sum(((x - opt) / (hi - lo)) ** 2))
+    es = CMAEvolutionStrategy(t._get_cma_x0(), 0.3 * float(np.exp(np.mean(np.log(hi - lo)))), lo, hi, seed=42, maxfevals=3000)
+    assert es.lam == 4 + int(3 * np.log(7)) and es.mu == es.lam // 2
+    while not es.stop():
+        X = es.ask()
+        assert len(X) == es.lam
+        es.tell(X, [es.penalised(x, f(es.repair(x))) for x in X])
+    assert es.best_f < 1e-9 and np.all(es.best_x >= lo) and np.all(es.best_x <= hi)
