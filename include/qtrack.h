@@ -320,6 +320,11 @@ int qt_rollout_policy(qt_context *ctx, const qt_params *params, int64_t E, int64
                       int64_t traj_stride, int64_t traj_slots, float *feat_out_dev, float *act_out_dev,
                       int64_t data_stride, int64_t data_slots);
 
+/* Self-test hook: the rollout's two-at-a-time square root (csrc/qt_step.cuh, sqrt_pair) on arbitrary
+ * arguments; must equal IEEE-754 sqrt bit for bit (tests/test_guards_gpu.py).                  */
+int qt_sqrt_pair_probe(qt_context *ctx, int64_t n, const double *a_dev, const double *b_dev,
+                       double *ra_out_dev, double *rb_out_dev);
+
 /* ---- measurement helper: register-resident DFMA loop, reports the achieved FP64 rate --------
  * Used as the FP64 roofline denominator by bench.py (MEASURED_PEAKS.json has no FP64 entry). */
 int qt_fp64_peak_probe(qt_context *ctx, int64_t iters, double *tflops_out_host,

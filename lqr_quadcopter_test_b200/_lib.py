@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "qt_reset_batched", "qt_rng_probe", "qt_observe_batched", "qt_compute_action_batched",
     "qt_step_batched", "qt_rollout", "qt_dare_batched", "qt_build_lqr_systems",
     "qt_reduce_scores", "qt_reduce_summary", "qt_evaluate_host", "qt_fp64_peak_probe",
-    "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy",
+    "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy", "qt_sqrt_pair_probe",
 )
 
 _lib = None
@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
             "qt_reduce_summary": (C.c_int, [vp, vp, i64, vp]),
             "qt_evaluate_host": (C.c_int, [vp, PP, vp, i64, i64, i64, vp, i32, vp]),
             "qt_fp64_peak_probe": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]),
+            "qt_sqrt_pair_probe": (C.c_int, [vp, i64, vp, vp, vp, vp]),
             "qt_mlp_packed_floats": (i64, [C.POINTER(QtMlp)]),
             "qt_policy_action_batched": (C.c_int, [vp, C.POINTER(QtMlp), i64, vp, vp]),
             "qt_rollout_policy": (C.c_int, [vp, PP, i64, i64, vp, vp, C.POINTER(QtMlp), vp, i32, i64, vp, vp, vp,
@@ -212,6 +213,9 @@ class Context:
         self.check(self.lib.qt_evaluate_host(
             self.handle, C.byref(params), _ptr(seeds_host), seeds_host.numel(), max_steps, chain,
             _ptr(K_host), k_cols, _ptr(metrics_host)))
+
+    def sqrt_pair_probe(self, a, b, ra_out, rb_out):
+        self.check(self.lib.qt_sqrt_pair_probe(self.handle, a.numel(), _ptr(a), _ptr(b), _ptr(ra_out), _ptr(rb_out)))
 
     def policy_action_batched(self, mlp, E, obs, action_out):
         self.check(self.lib.qt_policy_action_batched(self.handle, C.byref(mlp), E, _ptr(obs), _ptr(action_out)))

@@ -415,3 +415,26 @@ extern "C" int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t
     }
     return check_launch(ctx, "step_kernel");
 }
+
+// ---- self-test hook: the paired square root of qt_step.cuh against IEEE sqrt (tests/test_trig.py's GPU twin)
+namespace qt {
+__global__ void sqrt_pair_probe_kernel(int64_t n, const double *a, const double *b, double *ra, double *rb) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y;
+    sqrt_pair(a[i], b[i], x, y);
+    ra[i] = x;
+    rb[i] = y;
+}
+}  // namespace qt
+
+extern "C" int qt_sqrt_pair_probe(qt_context *ctx, int64_t n, const double *a_dev, const double *b_dev,
+                                  double *ra_out_dev, double *rb_out_dev) {
+    using namespace qt;
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, a_dev && b_dev && ra_out_dev && rb_out_dev && n >= 0, "null pointer / n < 0");
+    if (n == 0) return QT_OK;
+    DeviceGuard guard(ctx->device);
+    sqrt_pair_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, a_dev, b_dev, ra_out_dev, rb_out_dev);
+    return check_launch(ctx, "sqrt_pair_probe_kernel");
+}

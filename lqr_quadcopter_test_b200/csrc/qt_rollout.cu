@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             else
                 ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
 
-            // ---- metrics sample k = step (pre-step observation, eval.py:142-159)
+            // ---- metrics sample k = step (pre-step observation, eval.py:142-159); the control effort's
+            // square root is taken together with the tracking error's at the end of the step (sqrt_pair)
+            const double effort2 = act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3];
             {
                 const bool on = err_pre <= P.crit_target_radius;
                 met_on += on ? 1 : 0;
@@ -166,7 +168,6 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 cold[CR_SUM_ERR2 * T] += err_pre * err_pre;
                 const double mx = cold[CR_MAX_ERR * T];
                 if (step == 0 || err_pre > mx) cold[CR_MAX_ERR * T] = err_pre;
-                cold[CR_SUM_EFF * T] += sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
                 if (step > 0) {
                     if (prev_on && !on) {
                         in_phase = true;
@@ -237,7 +238,12 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
             t += C.dt;
             tg.template state<FULL>(P, t, tp, tv, ta);
-            err_post = norm3d(s[0] - tp[0], s[1] - tp[1], s[2] - tp[2]);
+            {
+                const double dx = s[0] - tp[0], dy = s[1] - tp[1], dz = s[2] - tp[2];
+                double effort;
+                sqrt_pair(dx * dx + dy * dy + dz * dz, effort2, err_post, effort);
+                cold[CR_SUM_EFF * T] += effort;
+            }
             term = termination_code(P, C, s, t);
             env_on += (err_post <= P.env_target_radius) ? 1 : 0;
             if constexpr (FULL) {

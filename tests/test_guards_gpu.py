@@ -106,3 +106,23 @@ def test_dare_stays_in_bounds(gpu_ctx, n, m, batch):
         res = A[i].T @ X[i] @ A[i] - X[i] - A[i].T @ X[i] @ B[i] @ G + Q[i]
         assert np.linalg.norm(res) / np.linalg.norm(X[i]) < 1e-10
         np.testing.assert_allclose(K.cpu().numpy()[i], G, rtol=1e-8, atol=1e-10)
+
+
+def test_paired_square_root_is_ieee_sqrt(gpu_ctx):
+    """qt_step.cuh sqrt_pair: bit-identical to correctly rounded sqrt, incl. the arguments that take the
+    library fallback (0, subnormal, huge, inf, NaN, negative) paired with ordinary ones."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.uniform(0, 4, 200000), 10.0 ** rng.uniform(-300, 300, 200000), rng.uniform(0, 1e-3, 100000) ** 4])
+    b = rng.permutation(a)
+    special = np.array([0.0, -0.0, 5e-324, 1e-310, 2.2250738585072014e-308, 1.7976931348623157e308, np.inf, np.nan, -1.0, 1.0])
+    a = np.concatenate([a, special, np.ones(10)])
+    b = np.concatenate([b, np.full(10, 2.0), special])
+    f64 = dict(dtype=torch.float64, device=gpu_ctx.device)
+    ta, tb = torch.as_tensor(a, **f64), torch.as_tensor(b, **f64)
+    ra, rb = torch.empty_like(ta), torch.empty_like(tb)
+    gpu_ctx.sqrt_pair_probe(ta, tb, ra, rb)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(ra.cpu().numpy(), np.sqrt(a))
+        np.testing.assert_array_equal(rb.cpu().numpy(), np.sqrt(b))
