@@ -5,11 +5,14 @@
 // (controllers/deep_tracking_policy.py:199-286, eval.py:119-165, train.py:668-721) by one kernel
 // launch for all episodes: one thread per episode, the env in fp64 exactly as in qt_rollout.cu (same
 // device functions), the network in fp32 like torch.  The packed weights are staged in shared memory
-// (they are read by every thread at the same address: broadcast loads), each thread keeps its
-// activations in its own column of two shared-memory tiles, and every output chunk of 16 units
-// accumulates in registers, so one weight vector load feeds four FFMAs.  This is batch-of-vectors
-// work with fp32-accuracy requirements (the parity target is torch's fp32 Linear); it stays on the
-// FP32 pipe.
+// (they are read by every thread at the same address: broadcast loads).  The 18 features stay in
+// registers for the first layer; hidden activations live in the thread's own column of a
+// shared-memory tile (two tiles, alternating, only when there are three or more hidden layers); every
+// chunk of 16 output units accumulates in registers, so one weight vector load feeds four FFMAs; and
+// the last hidden layer is never stored — each chunk of it is multiplied into the four output
+// accumulators as soon as it is activated.  For the default 64-64 network that leaves one 32 KB tile
+// + 22 KB of weights per block, i.e. four resident blocks per SM.  This is batch-of-vectors work with
+// fp32-accuracy requirements (the parity target is torch's fp32 Linear); it stays on the FP32 pipe.
 #include "qt_common.cuh"
 #include "qt_step.cuh"
 
@@ -26,7 +29,8 @@ struct MlpDesc {
     int w_off[QT_MLP_MAX_LAYERS];    // offset (floats) of Wt of layer l; the bias follows Wt
     int activation;
     int total_floats;
-    int max_width;                   // widest padded activation vector (>= 18)
+    int tile_w[2];                   // widths (floats per thread) of the two activation tiles: hidden layer l
+                                     // (0-based) is stored in tile l & 1; the last hidden layer is not stored
     float out_lo[4], out_scale[4];
 };
 
@@ -36,17 +40,17 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
     if (m.activation < QT_ACT_RELU || m.activation > QT_ACT_LEAKY_RELU) return false;
     d.n_layers = m.n_layers;
     d.activation = m.activation;
-    int off = 0, maxw = pad4(m.dims[0]);
+    int off = 0;
+    d.tile_w[0] = d.tile_w[1] = 0;
     for (int l = 0; l < m.n_layers; l++) {
         if (m.dims[l + 1] < 1 || m.dims[l + 1] > QT_MLP_MAX_WIDTH) return false;
         d.rows[l] = l == 0 ? m.dims[0] : pad4(m.dims[l]);
         d.outp[l] = pad4(m.dims[l + 1]);
         d.w_off[l] = off;
         off += d.rows[l] * d.outp[l] + d.outp[l];
-        if (d.outp[l] > maxw) maxw = d.outp[l];
+        if (l < m.n_layers - 2 && d.outp[l] > d.tile_w[l & 1]) d.tile_w[l & 1] = d.outp[l];  // stored hidden layers
     }
     d.total_floats = off;
-    d.max_width = maxw;
     for (int i = 0; i < 4; i++) {
         d.out_lo[i] = m.out_lo[i];
         d.out_scale[i] = m.out_scale[i];
@@ -54,19 +58,8 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
     return true;
 }
 
-__device__ __forceinline__ float activate(int kind, float x) {
-    switch (kind) {
-    case QT_ACT_TANH: return tanhf(x);
-    case QT_ACT_ELU: return x > 0.0f ? x : expm1f(x);
-    case QT_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.1f * x;
-    default: return fmaxf(x, 0.0f);  // torch.relu propagates NaN; fmaxf would not, handled below
-    }
-}
-
-// One chunk of CH (16 or 4) output units of one layer for this thread.
-template <int CH, int T>
-__device__ __forceinline__ void mlp_chunk(const float *__restrict__ Wt, const float *__restrict__ bias, int rows,
-                                          int outp, int j0, const float *xin, float (&acc)[CH]) {
+template <int CH>
+__device__ __forceinline__ void chunk_bias(const float *__restrict__ bias, int j0, float (&acc)[CH]) {
 #pragma unroll
     for (int i = 0; i < CH; i += 4) {
         const float4 b = *reinterpret_cast<const float4 *>(bias + j0 + i);
@@ -75,81 +68,135 @@ __device__ __forceinline__ void mlp_chunk(const float *__restrict__ Wt, const fl
         acc[i + 2] = b.z;
         acc[i + 3] = b.w;
     }
-    const float *w = Wt + j0;
-#pragma unroll 2
-    for (int k = 0; k < rows; k++) {
-        const float xk = xin[k * T];
+}
+
+template <int CH>
+__device__ __forceinline__ void chunk_fma(const float *__restrict__ w, float xk, float (&acc)[CH]) {
 #pragma unroll
-        for (int i = 0; i < CH; i += 4) {
-            const float4 wk = *reinterpret_cast<const float4 *>(w + i);
-            acc[i] = fmaf(xk, wk.x, acc[i]);
-            acc[i + 1] = fmaf(xk, wk.y, acc[i + 1]);
-            acc[i + 2] = fmaf(xk, wk.z, acc[i + 2]);
-            acc[i + 3] = fmaf(xk, wk.w, acc[i + 3]);
-        }
+    for (int i = 0; i < CH; i += 4) {
+        const float4 wk = *reinterpret_cast<const float4 *>(w + i);
+        acc[i] = fmaf(xk, wk.x, acc[i]);
+        acc[i + 1] = fmaf(xk, wk.y, acc[i + 1]);
+        acc[i + 2] = fmaf(xk, wk.z, acc[i + 2]);
+        acc[i + 3] = fmaf(xk, wk.w, acc[i + 3]);
+    }
+}
+
+// One chunk of CH (16 or 4) output units of one layer for this thread; the layer input is this thread's
+// column of a shared-memory tile (xin[k * T]).
+template <int CH, int T>
+__device__ __forceinline__ void mlp_chunk(const float *__restrict__ Wt, const float *__restrict__ bias, int rows,
+                                          int outp, int j0, const float *xin, float (&acc)[CH]) {
+    chunk_bias<CH>(bias, j0, acc);
+    const float *w = Wt + j0;
+#pragma unroll 4
+    for (int k = 0; k < rows; k++) {
+        chunk_fma<CH>(w, xin[k * T], acc);
         w += outp;
     }
 }
 
-// PolicyNetwork.forward (deep_tracking_policy.py:114-147) for one feature vector held in xa[k * T].
-// xa / xb: this thread's columns of the two activation tiles.  W: packed weights (shared or global).
+// The same for the first layer: its 18 inputs are in registers.
+template <int CH>
+__device__ __forceinline__ void mlp_chunk_first(const float *__restrict__ Wt, const float *__restrict__ bias,
+                                                int outp, int j0, const float (&feat)[QT_FEATURE_DIM], float (&acc)[CH]) {
+    chunk_bias<CH>(bias, j0, acc);
+    const float *w = Wt + j0;
+#pragma unroll
+    for (int k = 0; k < QT_FEATURE_DIM; k++) chunk_fma<CH>(w + k * outp, feat[k], acc);
+}
+
+template <int KIND>
+__device__ __forceinline__ float activate_t(float x) {
+    if (KIND == QT_ACT_TANH) return tanhf(x);
+    if (KIND == QT_ACT_ELU) return x > 0.0f ? x : expm1f(x);
+    if (KIND == QT_ACT_LEAKY_RELU) return x > 0.0f ? x : 0.1f * x;
+    return x != x ? x : fmaxf(x, 0.0f);   // torch.relu propagates NaN, fmaxf does not
+}
+
+// Activate a finished chunk and either store it (hidden layer) or multiply it into the output
+// accumulators (last hidden layer, fused output layer).  The activation kind is dispatched once per
+// chunk, not per element.
+template <int KIND, int CH, int T>
+__device__ __forceinline__ void finish_chunk_t(const float (&acc)[CH], bool last_hidden, const float *__restrict__ Wo,
+                                               int j0, float *xout, float (&o)[4]) {
+    if (last_hidden) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) chunk_fma<4>(Wo + (j0 + i) * 4, activate_t<KIND>(acc[i]), o);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CH; i++) xout[(j0 + i) * T] = activate_t<KIND>(acc[i]);
+    }
+}
+
+template <int CH, int T>
+__device__ __forceinline__ void finish_chunk(int kind, const float (&acc)[CH], bool last_hidden,
+                                             const float *__restrict__ Wo, int j0, float *xout, float (&o)[4]) {
+    switch (kind) {
+    case QT_ACT_TANH: finish_chunk_t<QT_ACT_TANH, CH, T>(acc, last_hidden, Wo, j0, xout, o); break;
+    case QT_ACT_ELU: finish_chunk_t<QT_ACT_ELU, CH, T>(acc, last_hidden, Wo, j0, xout, o); break;
+    case QT_ACT_LEAKY_RELU: finish_chunk_t<QT_ACT_LEAKY_RELU, CH, T>(acc, last_hidden, Wo, j0, xout, o); break;
+    default: finish_chunk_t<QT_ACT_RELU, CH, T>(acc, last_hidden, Wo, j0, xout, o); break;
+    }
+}
+
+// PolicyNetwork.forward (deep_tracking_policy.py:114-147) for one feature vector held in registers.
+// tile0 / tile1: this thread's columns of the two activation tiles.  W: packed weights (shared or global).
 template <int T>
-__device__ __forceinline__ void mlp_forward(const MlpDesc &M, const float *__restrict__ W, float *xa, float *xb,
-                                            float (&out)[4]) {
-    float *xin = xa, *xout = xb;
-    for (int l = 0; l < M.n_layers; l++) {
+__device__ __forceinline__ void mlp_forward(const MlpDesc &M, const float *__restrict__ W, float *tile0, float *tile1,
+                                            const float (&feat)[QT_FEATURE_DIM], float (&out)[4]) {
+    const int L = M.n_layers;                      // linear layers; hidden layers are 0 .. L-2
+    const float *Wo = W + M.w_off[L - 1];          // output layer: Wt [rows][4], bias [4]
+    const int rows_o = M.rows[L - 1];
+    float o[4];
+    chunk_bias<4>(Wo + rows_o * 4, 0, o);
+    if (L == 1) {                                  // no hidden layer: a linear policy
+#pragma unroll
+        for (int k = 0; k < QT_FEATURE_DIM; k++) chunk_fma<4>(Wo + k * 4, feat[k], o);
+    }
+    for (int l = 0; l + 1 < L; l++) {
         const float *Wt = W + M.w_off[l];
         const int rows = M.rows[l], outp = M.outp[l];
         const float *bias = Wt + rows * outp;
-        if (l == M.n_layers - 1) {
-            float acc[4];
-            mlp_chunk<4, T>(Wt, bias, rows, outp, 0, xin, acc);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float sg = 1.0f / (1.0f + expf(-acc[i]));  // torch.sigmoid
-                out[i] = fmaf(sg, M.out_scale[i], M.out_lo[i]);
-            }
-            return;
-        }
+        const float *xin = ((l - 1) & 1) ? tile1 : tile0;
+        float *xout = (l & 1) ? tile1 : tile0;
+        const bool last_hidden = (l == L - 2);
         int j0 = 0;
         for (; j0 + 16 <= outp; j0 += 16) {
             float acc[16];
-            mlp_chunk<16, T>(Wt, bias, rows, outp, j0, xin, acc);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                float a = activate(M.activation, acc[i]);
-                if (M.activation == QT_ACT_RELU && acc[i] != acc[i]) a = acc[i];
-                xout[(j0 + i) * T] = a;
-            }
+            if (l == 0)
+                mlp_chunk_first<16>(Wt, bias, outp, j0, feat, acc);
+            else
+                mlp_chunk<16, T>(Wt, bias, rows, outp, j0, xin, acc);
+            finish_chunk<16, T>(M.activation, acc, last_hidden, Wo, j0, xout, o);
         }
         for (; j0 < outp; j0 += 4) {
             float acc[4];
-            mlp_chunk<4, T>(Wt, bias, rows, outp, j0, xin, acc);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float a = activate(M.activation, acc[i]);
-                if (M.activation == QT_ACT_RELU && acc[i] != acc[i]) a = acc[i];
-                xout[(j0 + i) * T] = a;
-            }
+            if (l == 0)
+                mlp_chunk_first<4>(Wt, bias, outp, j0, feat, acc);
+            else
+                mlp_chunk<4, T>(Wt, bias, rows, outp, j0, xin, acc);
+            finish_chunk<4, T>(M.activation, acc, last_hidden, Wo, j0, xout, o);
         }
-        float *t = xin;
-        xin = xout;
-        xout = t;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float sg = 1.0f / (1.0f + expf(-o[i]));  // torch.sigmoid
+        out[i] = fmaf(sg, M.out_scale[i], M.out_lo[i]);
     }
 }
 
 // deep_tracking_policy.py:241-286: fp64 differences first, then the fp32 cast
-template <int T>
-__device__ __forceinline__ void write_features(const double (&s)[12], const double (&tp)[3], const double (&tv)[3],
-                                               float *x) {
+__device__ __forceinline__ void make_features(const double (&s)[12], const double (&tp)[3], const double (&tv)[3],
+                                              float (&x)[QT_FEATURE_DIM]) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        x[i * T] = (float)(tp[i] - s[i]);
-        x[(3 + i) * T] = (float)(tv[i] - s[3 + i]);
-        x[(6 + i) * T] = (float)s[6 + i];
-        x[(9 + i) * T] = (float)s[9 + i];
-        x[(12 + i) * T] = (float)tp[i];
-        x[(15 + i) * T] = (float)tv[i];
+        x[i] = (float)(tp[i] - s[i]);
+        x[3 + i] = (float)(tv[i] - s[3 + i]);
+        x[6 + i] = (float)s[6 + i];
+        x[9 + i] = (float)s[9 + i];
+        x[12 + i] = (float)tp[i];
+        x[15 + i] = (float)tv[i];
     }
 }
 
@@ -163,17 +210,20 @@ struct PolicyArgs {
     int traj_stride, traj_slots, data_stride, data_slots;
 };
 
-// Stage the packed weights; returns the pointer the threads should read them through.
-__device__ __forceinline__ const float *stage_weights(const MlpDesc &M, const float *Wg, int in_smem, float *smem_w) {
-    if (!in_smem) return Wg;
+// Stage the packed weights at the start of shared memory (when they fit).
+__device__ __forceinline__ void stage_weights(const MlpDesc &M, const float *Wg, int in_smem, float *smem_w) {
+    if (!in_smem) return;
     for (int i = threadIdx.x * 4; i < M.total_floats; i += blockDim.x * 4)
         *reinterpret_cast<float4 *>(smem_w + i) = *reinterpret_cast<const float4 *>(Wg + i);
     __syncthreads();
-    return smem_w;
 }
 
-template <int MOTION>
-__global__ void __launch_bounds__(kPolicyThreads, 2)
+// MINB = resident blocks per SM the register allocator must allow.  Measured (2^18 episodes): with the
+// weights in shared memory three blocks of 168 registers beat two of 255 (64-64 network 2.40e9 against
+// 2.19e9 env-steps/s); when the weights are too large to stage and stream from L1/L2 instead, the deeper
+// load prefetch that 255 registers allow wins (128-128: 4.0e8 against 2.4e8).
+template <int MOTION, int MINB>
+__global__ void __launch_bounds__(kPolicyThreads, MINB)
     rollout_policy_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                           const __grid_constant__ MlpDesc M, const __grid_constant__ PolicyArgs A) {
     extern __shared__ __align__(16) float smem_f[];
@@ -181,9 +231,9 @@ __global__ void __launch_bounds__(kPolicyThreads, 2)
     const int64_t E = A.E;
     const int64_t e = (int64_t)blockIdx.x * T + threadIdx.x;
     const int w_floats = A.w_in_smem ? ((M.total_floats + 3) & ~3) : 0;
-    const float *W = stage_weights(M, A.W, A.w_in_smem, smem_f);
-    float *xa = smem_f + w_floats + threadIdx.x;
-    float *xb = xa + M.max_width * T;
+    stage_weights(M, A.W, A.w_in_smem, smem_f);
+    float *tile0 = smem_f + w_floats + threadIdx.x;
+    float *tile1 = tile0 + M.tile_w[0] * T;
     if (e >= E) return;
 
     double s[12];
@@ -214,16 +264,19 @@ __global__ void __launch_bounds__(kPolicyThreads, 2)
 
     while (term == QT_TERM_NONE && step < A.max_steps) {
         // ---- the policy acts on the pre-step observation
-        write_features<T>(s, tp, tv, xa);
+        float feat[QT_FEATURE_DIM];
+        make_features(s, tp, tv, feat);
         const bool log_data = A.feat && step == next_data && data_slot < A.data_slots;
-        if (log_data) {  // before the forward pass: the activation tiles are reused by the layers
+        if (log_data) {
             float *f = A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM;
 #pragma unroll
-            for (int i = 0; i < QT_FEATURE_DIM; i += 2)
-                *reinterpret_cast<float2 *>(f + i) = make_float2(xa[i * T], xa[(i + 1) * T]);
+            for (int i = 0; i < QT_FEATURE_DIM; i += 2) *reinterpret_cast<float2 *>(f + i) = make_float2(feat[i], feat[i + 1]);
         }
         float out[4];
-        mlp_forward<T>(M, W, xa, xb, out);
+        if (A.w_in_smem)   // two inlined copies: one reads the weights with LDS, the other with LDG
+            mlp_forward<T>(M, smem_f, tile0, tile1, feat, out);
+        else
+            mlp_forward<T>(M, A.W, tile0, tile1, feat, out);
         double act[4] = {(double)out[0], (double)out[1], (double)out[2], (double)out[3]};
 
         // ---- supervisor label on the same observation (train.py:682-696)
@@ -358,9 +411,9 @@ __global__ void __launch_bounds__(kPolicyThreads)
     const int64_t E = A.E;
     const int64_t e = (int64_t)blockIdx.x * T + threadIdx.x;
     const int w_floats = A.w_in_smem ? ((M.total_floats + 3) & ~3) : 0;
-    const float *W = stage_weights(M, A.W, A.w_in_smem, smem_f);
-    float *xa = smem_f + w_floats + threadIdx.x;
-    float *xb = xa + M.max_width * T;
+    stage_weights(M, A.W, A.w_in_smem, smem_f);
+    float *tile0 = smem_f + w_floats + threadIdx.x;
+    float *tile1 = tile0 + M.tile_w[0] * T;
     if (e >= E) return;
     double s[12], tp[3], tv[3];
 #pragma unroll
@@ -370,18 +423,22 @@ __global__ void __launch_bounds__(kPolicyThreads)
         tp[i] = A.obs[(int64_t)(12 + i) * E + e];
         tv[i] = A.obs[(int64_t)(15 + i) * E + e];
     }
-    write_features<T>(s, tp, tv, xa);
+    float feat[QT_FEATURE_DIM];
+    make_features(s, tp, tv, feat);
     float out[4];
-    mlp_forward<T>(M, W, xa, xb, out);
+    if (A.w_in_smem)
+        mlp_forward<T>(M, smem_f, tile0, tile1, feat, out);
+    else
+        mlp_forward<T>(M, A.W, tile0, tile1, feat, out);
 #pragma unroll
     for (int i = 0; i < 4; i++) A.action[(int64_t)i * E + e] = (double)out[i];
 }
 
-// shared memory plan: [weights if they fit][2 activation tiles of max_width x T floats]
+// shared memory plan: [weights if they fit][activation tile 0][activation tile 1]
 static size_t smem_plan(const MlpDesc &M, int &w_in_smem) {
-    const size_t act = 2 * (size_t)M.max_width * kPolicyThreads * sizeof(float);
+    const size_t act = (size_t)(M.tile_w[0] + M.tile_w[1]) * kPolicyThreads * sizeof(float);
     const size_t w = (((size_t)M.total_floats + 3) & ~(size_t)3) * sizeof(float);
-    const size_t budget = 100 * 1024;  // two blocks per SM
+    const size_t budget = 100 * 1024;  // at least two blocks per SM
     w_in_smem = (act + w <= budget) ? 1 : 0;
     return act + (w_in_smem ? w : 0);
 }
@@ -390,10 +447,16 @@ template <int MOTION>
 static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, const PolicyArgs &A, size_t smem, cudaStream_t st) {
     DynConsts C;
     C.init(P);
-    cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const int64_t blocks = (A.E + kPolicyThreads - 1) / kPolicyThreads;
-    rollout_policy_kernel<MOTION><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    if (A.w_in_smem && smem <= 72 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rollout_policy_kernel<MOTION, 3><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rollout_policy_kernel<MOTION, 2><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    }
     return cudaGetLastError();
 }
 

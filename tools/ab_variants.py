@@ -47,8 +47,36 @@ def run(E):
         env = dict(os.environ)
         if lib is not None:
             env["QTRACK_LIB"] = str(lib)
-        r = subprocess.run([sys.executable, __file__, "one", str(E)], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, __file__, MODE, str(E)], env=env, capture_output=True, text=True)
         print(f"{'default' if lib is None else lib.stem[10:]:24s} {r.stdout.strip() or r.stderr[-400:]}", flush=True)
+
+
+def one_policy(E):
+    import torch
+
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy, EnvConfig, SuccessCriteria, _lib, rollout_device
+
+    ctx = _lib.get_context()
+    seeds = torch.arange(E, dtype=torch.int64, device=ctx.device) + 42
+    res = []
+    for hidden in ([64, 64], [32], [128, 128]):
+        torch.manual_seed(0)
+        pol = DeepTrackingPolicy(config={"hidden_sizes": hidden})
+        env = EnvConfig()
+        env.target.motion_type = "linear"
+        for _ in range(2):
+            rollout_device(pol, env, SuccessCriteria(), seeds)
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record()
+        for i in range(3):
+            r = rollout_device(pol, env, SuccessCriteria(), seeds)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(3))[1]
+        steps = float(r["metrics"][0].sum().item())
+        res.append(f"{hidden}: {steps / ms * 1e3:.3e} steps/s ({ms:.0f} ms)")
+    print("   ".join(res))
 
 
 def one(E):
@@ -81,10 +109,17 @@ def one(E):
     print("   ".join(res))
 
 
+MODE = "one"
+
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build(sys.argv[2:])
     elif sys.argv[1] == "run":
         run(int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20)
+    elif sys.argv[1] == "run_policy":
+        MODE = "one_policy"
+        run(int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18)
+    elif sys.argv[1] == "one_policy":
+        one_policy(int(sys.argv[2]))
     else:
         one(int(sys.argv[2]))
