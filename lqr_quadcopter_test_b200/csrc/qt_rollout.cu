@@ -42,7 +42,7 @@ struct RolloutArgs {
 // integrator needs ~110 registers at its widest point, and keeping the cold state out of the
 // register file is what lets four 128-thread blocks (16 warps) stay resident per SM without
 // spilling.  Column access (row * blockDim + threadIdx) is conflict free.
-enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_MAX_ERR, CR_OV_CUR, CR_OV_MAX, CR_TARGET };
+enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_OV_CUR, CR_OV_MAX, CR_TARGET };
 constexpr int kColdRows = CR_TARGET + QT_TARGET_PARAMS;
 
 template <int MOTION, int CTRL, bool FULL>
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     constexpr int T = kRolloutThreads;
     const int64_t E = A.E;
     const int64_t chain_id = (int64_t)blockIdx.x * T + threadIdx.x;
-    double *sK = smem;
-    double *cold = smem + A.k_smem_doubles + threadIdx.x;  // this thread's column: cold[row * T]
+    double *cold = smem + threadIdx.x;   // this thread's column of the cold tile: cold[row * T]
+    double *sK = smem + kColdRows * T;   // staged gains follow the tile (compile-time offset)
 
     int64_t g0 = 0;
     if (A.k_in_smem) {
@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         cold[CR_SUM_ERR * T] = 0.0;
         cold[CR_SUM_ERR2 * T] = 0.0;
         cold[CR_SUM_EFF * T] = 0.0;
-        cold[CR_MAX_ERR * T] = 0.0;
         cold[CR_OV_CUR * T] = 0.0;
         cold[CR_OV_MAX * T] = 0.0;
         // overshoot detector state (utils/metrics.py:205-261), streamed
@@ -121,6 +120,9 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         double tp[3], tv[3], ta[3];
         tg.template state<FULL>(P, t, tp, tv, ta);
         double err_pre = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
+        // np.max of the pre-step errors (utils/metrics.py:329).  Sample 0 initialises it; later samples are
+        // never NaN (a non-finite state ends the episode before it is sampled), so a plain compare suffices
+        double max_err = err_pre;
         Trig B;  // sin/cos of the current attitude, carried from step to step (trig_rebase)
         {
             const double e0[3] = {s[6], s[7], s[8]};
@@ -166,17 +168,17 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 met_on += on ? 1 : 0;
                 cold[CR_SUM_ERR * T] += err_pre;
                 cold[CR_SUM_ERR2 * T] += err_pre * err_pre;
-                const double mx = cold[CR_MAX_ERR * T];
-                if (step == 0 || err_pre > mx) cold[CR_MAX_ERR * T] = err_pre;
-                if (step > 0) {
-                    if (prev_on && !on) {
+                max_err = err_pre > max_err ? err_pre : max_err;
+                // overshoot detector: nothing to do while the vehicle stays on target (or has never been)
+                if (in_phase | (prev_on & !on)) {
+                    if (!in_phase) {            // prev_on && !on: a departure starts
                         in_phase = true;
                         streak = 1;
                         cold[CR_OV_CUR * T] = err_pre - P.crit_target_radius;
-                    } else if (in_phase && !on) {
+                    } else if (!on) {
                         streak += 1;
                         cold[CR_OV_CUR * T] = fmax(cold[CR_OV_CUR * T], err_pre - P.crit_target_radius);
-                    } else if (in_phase && on) {
+                    } else {
                         if (streak >= P.overshoot_window) {
                             ov_count += 1;
                             cold[CR_OV_MAX * T] = fmax(cold[CR_OV_MAX * T], cold[CR_OV_CUR * T]);
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         m[(int64_t)QT_M_ENV_ON_TARGET * E] = (double)env_on;
         m[(int64_t)QT_M_MET_ON_TARGET * E] = (double)met_on;
         m[(int64_t)QT_M_SUM_ERR * E] = cold[CR_SUM_ERR * T];
-        m[(int64_t)QT_M_MAX_ERR * E] = cold[CR_MAX_ERR * T];
+        m[(int64_t)QT_M_MAX_ERR * E] = step > 0 ? max_err : 0.0;
         m[(int64_t)QT_M_SUM_ERR2 * E] = cold[CR_SUM_ERR2 * T];
         m[(int64_t)QT_M_SUM_EFFORT * E] = cold[CR_SUM_EFF * T];
         m[(int64_t)QT_M_OVERSHOOT_COUNT * E] = (double)ov_count;
@@ -393,7 +395,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
             A.k_smem_doubles = (int)doubles;
         }
     }
-    // staged gains + the per-thread cold-state tile (kColdRows x 128 doubles = 18 KB)
+    // the per-thread cold-state tile (kColdRows x 128 doubles = 17 KB) + staged gains
     const size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
     const bool full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 ||
                       traj_out_dev != nullptr || feat_out_dev != nullptr;
