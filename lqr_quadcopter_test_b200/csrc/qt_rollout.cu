@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             violations += A.env_bounds_check ? validate_action<true>(P, act, actv) : validate_action<false>(P, act, actv);
             if (euler)
                 integrate<true, FAST>(C, s, actv, B, eta_old);
+            else if (QT_OPT_FLAT_RK4)
+                integrate_flat<FAST>(C, s, actv, B, eta_old);
             else
                 integrate<false, FAST>(C, s, actv, B, eta_old);
             constrain_state<FAST>(P, C, s);
