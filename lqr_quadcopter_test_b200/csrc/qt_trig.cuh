@@ -112,8 +112,16 @@ QT_TRIG_FN void sincos_pi(double x, double &s, double &c) {
 // two Taylor terms fewer per polynomial, truncation error < 4e-19).
 // TIER 0: |d| <= kShiftMax, 1: |d| <= kShiftSmall, 2: |d| <= kShiftTiny
 template <int TIER>
+QT_TRIG_FN void sincos_shifted_d(double sb, double cb, double d, double &s, double &c);
+
+template <int TIER>
 QT_TRIG_FN void sincos_shifted(double base, double sb, double cb, double arg, double &s, double &c) {
-    const double d = arg - base;  // exact (Sterbenz) or the increment itself when base is tiny
+    sincos_shifted_d<TIER>(sb, cb, arg - base, s, c);  // exact (Sterbenz) or the increment itself when base is tiny
+}
+
+// The same with the increment given directly: sin/cos(b + d) from sin/cos(b).
+template <int TIER>
+QT_TRIG_FN void sincos_shifted_d(double sb, double cb, double d, double &s, double &c) {
     const double z = d * d;
     if (TIER == 2) {
         const double sd = fma(d * z, c_trig[16], d);              // d - d^3/6
