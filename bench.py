@@ -19,6 +19,8 @@ scaling: every rank gets its own 2^20 episodes (seeds disjoint).  Prints ONE JSO
   cpu_baseline  the CPU oracle (C restatement of the reference's loop, all host threads) on a bounded
              sample of the same workload — a reported baseline, not the optimisation target
   dare       batched DARE throughput (second headline metric): 65 536 n=6 systems per launch
+  policy     SURVEY §8(f).2: the same closed loop driven by the 64-64 deep tracking policy (fp32 network in
+             the kernel) on 2^17 episodes, with the Riccati supervisor labelling every 10th step
 """
 from __future__ import annotations
 
@@ -184,6 +186,12 @@ def run_reference_arm(args) -> None:
                 "travel to the GPU box, so this arm times its C restatement, a far stronger CPU baseline.",
     }
     print(json.dumps(line))
+
+
+def ctx_sm_count(ctx) -> int:
+    import torch
+
+    return torch.cuda.get_device_properties(ctx.device).multi_processor_count
 
 
 # ---------------------------------------------------------------------------------- GPU arm --
@@ -354,6 +362,39 @@ def run_gpu_arm(args) -> None:
                          "frac": dare_tflops / fp64_tflops if fp64_tflops > 0 else None,
                          "flops_per_solve": w_dare(DARE_N, 4, mean_iters)}}
 
+    # deep policy in the loop (random-init 64-64 network, torch seed 0; linear target; labels every 10th step)
+    policy = None
+    try:
+        from lqr_quadcopter_test_b200 import DeepTrackingPolicy, rollout_device
+
+        torch.manual_seed(0)
+        pol = DeepTrackingPolicy(config={"hidden_sizes": [64, 64], "activation": "relu"})
+        Ep = min(E, 1 << 17)
+        pseeds = torch.arange(Ep, dtype=torch.int64, device=dev) + 42
+        for _ in range(2):
+            rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            pout = rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
+        p1.record()
+        torch.cuda.synchronize()
+        p_ms = p0.elapsed_time(p1) / 3
+        p_steps = float(pout["metrics"][0].sum().item())
+        fma_per_step = 18 * 64 + 64 * 64 + 64 * 4
+        fp32_peak = ctx_sm_count(ctx) * 128 * 2 * (clock_info.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        policy = {"metric": "closed-loop env-steps/s with the 64-64 deep tracking policy acting (fp32, in-kernel)",
+                  "value": p_steps / (p_ms * 1e-3), "unit": "env-steps/s", "episodes": Ep, "ms_per_launch": p_ms,
+                  "includes": "reset + rollout + supervisor labels and 18+4 fp32 data-set rows every 10th step",
+                  "roofline": {"bound": "fp32", "achieved": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12,
+                               "peak": fp32_peak, "unit": "TFLOP/s",
+                               "frac": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12 / fp32_peak,
+                               "peak_source": "nominal: SMs x 128 FP32 lanes x 2 x max SM clock (no measured FP32 figure)",
+                               "algorithmic_flops_per_env_step": 2 * fma_per_step}}
+    except Exception as exc:  # the headline line must not be lost to the secondary section
+        policy = {"error": repr(exc)}
+
     cores = os.cpu_count() or 1
     sample_eps = sized_cpu_sample(10.0, cores)
     cpu_rate, cpu_s = cpu_port_rate(sample_eps, cores)
@@ -374,7 +415,7 @@ def run_gpu_arm(args) -> None:
                 "d2h_bytes_per_step": 16 * 8 * E, "api": "qt_evaluate_host (C ABI, pinned host buffers)",
                 "matches_device_resident_result": same},
         "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare, "policy": policy,
     }
     print(json.dumps(line))
     if world > 1:
