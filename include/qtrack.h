@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QT_ABI_VERSION 3
+#define QT_ABI_VERSION 4
 
 #define QT_STATE_DIM 12     /* env/quadcopter_env.py:63-70  [p(3) v(3) roll,pitch,yaw  p,q,r] */
 #define QT_ACTION_DIM 4     /* thrust, roll_rate, pitch_rate, yaw_rate (controllers/base.py:28) */
@@ -231,14 +231,17 @@ int qt_step_batched(qt_context *ctx, const qt_params *params, int64_t E, double 
  *   final_state_out [12][E] or NULL,
  *   traj_out [slots][24][E] or NULL: steps k with k % traj_stride == 0, slot = k / traj_stride,
  *   feat_out f32 [slots][E][18] and act_out f32 [slots][E][4] or NULL (teacher data set,
- *   deep_tracking_policy.py:241-286 / train.py:683-696), every data_stride-th step.         */
+ *   deep_tracking_policy.py:241-286 / train.py:683-696), every data_stride-th step,
+ *   ff_gains [groups][6] or NULL: per-group feedforward gains (velocity x,y,z then acceleration
+ *   x,y,z) replacing params->ff_velocity_gain / ff_acceleration_gain when feedforward is enabled -
+ *   a tuner batch whose candidates differ in those gains (tuning.py:700-712); same grouping as K. */
 int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
                int64_t chain, const double *state0_dev, const double *tparams_dev,
                const double *K_dev, int32_t k_cols, int64_t k_stride, double *metrics_out_dev,
                double *ctrl_state_io_dev, double *final_state_out_dev, double *traj_out_dev,
                int64_t traj_stride,
                int64_t traj_slots, float *feat_out_dev, float *act_out_dev,
-               int64_t data_stride, int64_t data_slots);
+               int64_t data_stride, int64_t data_slots, const double *ff_gains_dev);
 
 /* ---- A11: solve_dare -----------------------------------------------------------------------
  * riccati_lqr.py:119-184 for `batch` systems: P solves A'PA - P - A'PB(R+B'PB)^-1 B'PA + Q = 0,

@@ -66,7 +66,7 @@ def load_library() -> C.CDLL:
             "qt_step_batched": (C.c_int, [vp, PP, i64, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp,
                                           vp, vp, vp, vp, vp]),
             "qt_rollout": (C.c_int, [vp, PP, i64, i64, i64, vp, vp, vp, i32, i64, vp, vp, vp, vp,
-                                     i64, i64, vp, vp, i64, i64]),
+                                     i64, i64, vp, vp, i64, i64, vp]),
             "qt_dare_batched": (C.c_int, [vp, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp,
                                           vp, vp, vp]),
             "qt_build_lqr_systems": (C.c_int, [vp, i32, i64, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp]),
@@ -183,12 +183,12 @@ class Context:
 
     def rollout(self, params, E, max_steps, chain, state0, tparams, K, k_cols, k_stride,
                 metrics_out, ctrl_state_io=None, final_state_out=None, traj_out=None, traj_stride=1,
-                traj_slots=0, feat_out=None, act_out=None, data_stride=1, data_slots=0):
+                traj_slots=0, feat_out=None, act_out=None, data_stride=1, data_slots=0, ff_gains=None):
         self.check(self.lib.qt_rollout(
             self.handle, C.byref(params), E, max_steps, chain, _ptr(state0), _ptr(tparams),
             _ptr(K), k_cols, k_stride, _ptr(metrics_out), _ptr(ctrl_state_io),
             _ptr(final_state_out), _ptr(traj_out),
-            traj_stride, traj_slots, _ptr(feat_out), _ptr(act_out), data_stride, data_slots))
+            traj_stride, traj_slots, _ptr(feat_out), _ptr(act_out), data_stride, data_slots, _ptr(ff_gains)))
 
     def dare_batched(self, n, m, batch, A, strideA, B, strideB, Q, strideQ, R, strideR, P_out,
                      K_out, iters_out, info_out):

@@ -156,7 +156,7 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     int rc = qt_reset_batched(ctx, params, seeds_dev, E, nullptr, state_dev, tp_dev);
     if (rc) return rc;
     rc = qt_rollout(ctx, params, E, max_steps, chain, state_dev, tp_dev, K_dev, k_cols, E, met_dev, nullptr,
-                    nullptr, nullptr, 1, 0, nullptr, nullptr, 1, 0);
+                    nullptr, nullptr, 1, 0, nullptr, nullptr, 1, 0, nullptr);
     if (rc) return rc;
     QT_CUDA_TRY(ctx, cudaMemcpyAsync(metrics_host, met_dev, 16 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     QT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

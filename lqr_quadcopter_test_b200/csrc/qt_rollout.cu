@@ -32,6 +32,7 @@ struct RolloutArgs {
     int k_smem_doubles;  // doubles reserved for the staged gains at the start of shared memory
     int env_bounds_check;  // 0 when the controller's clamps lie inside the env's action limits
     const double *state0, *tparams, *K;
+    const double *ff;  // optional per-group feedforward gains [groups][6], NULL = qt_params'
     double *metrics, *ctrl_state, *final_state, *traj;
     float *feat, *actf;
     int traj_stride, traj_slots, data_stride, data_slots;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         tg.load(cold + CR_TARGET * T, A.tparams, E, e);
         const int64_t grp = e / A.k_stride;
         const double *Kp = A.k_in_smem ? (sK + (grp - g0) * 4 * KC) : (A.K + grp * 4 * KC);
+        const double *ffg = (FULL && A.ff) ? A.ff + grp * 6 : nullptr;
         if (A.chain == 1) {  // controller.reset() before every episode (tuning.py:879)
             integ[0] = integ[1] = integ[2] = 0.0;
             saturations = 0;
@@ -156,9 +158,9 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             // ---- controller on the pre-step observation
             double act[4];
             if constexpr (CTRL == CK_PID)
-                pid_action<FULL>(P, Kp, s, tp, tv, ta, t, integ, last_time, act);
+                pid_action<FULL>(P, Kp, s, tp, tv, ta, t, integ, last_time, act, ffg);
             else
-                ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act);
+                ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act, ffg);
 
             // ---- metrics sample k = step (pre-step observation, eval.py:142-159); the control effort's
             // square root is taken together with the tracking error's at the end of the step (sqrt_pair)
@@ -346,7 +348,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
                           double *final_state_out_dev, double *traj_out_dev, int64_t traj_stride,
                           int64_t traj_slots,
                           float *feat_out_dev, float *act_out_dev, int64_t data_stride,
-                          int64_t data_slots) {
+                          int64_t data_slots, const double *ff_gains_dev) {
     using namespace qt;
     if (!ctx) return QT_ERR_ARG;
     QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
@@ -372,6 +374,7 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     A.state0 = state0_dev;
     A.tparams = tparams_dev;
     A.K = K_dev;
+    A.ff = params->feedforward_enabled ? ff_gains_dev : nullptr;
     A.metrics = metrics_out_dev;
     A.ctrl_state = ctrl_state_io_dev;
     A.final_state = final_state_out_dev;

@@ -311,10 +311,11 @@ class ControllerTuner:
 
     @staticmethod
     def _batchable(configs: list[dict]) -> bool:
-        """A batch shares one qt_params block, so feedforward gains / LQI mode must agree."""
+        """A batch shares one qt_params block: LQI mode and the feedforward switch must agree (the
+        feedforward gains themselves travel per candidate, qt_rollout's ff_gains)."""
         lqi = {bool(c.get("use_lqi", False)) for c in configs}
-        ff = any(c.get("feedforward_enabled", False) for c in configs)
-        return len(lqi) == 1 and not ff
+        ff = {bool(c.get("feedforward_enabled", False)) for c in configs}
+        return len(lqi) == 1 and len(ff) == 1
 
     def evaluate_configs(self, configs: list[dict]) -> tuple[list[float], list[dict]]:
         """Score every candidate configuration: returns (scores, metrics dictionaries)."""
@@ -392,8 +393,15 @@ class ControllerTuner:
         tparams = tp.repeat(1, C).contiguous()
         E = C * eps
         metrics = torch.empty((16, E), **f64)
+        ff_gains = None
+        if proto.feedforward_enabled:   # per-candidate feedforward gains (tuning.py:700-712)
+            ffh = np.zeros((C, 6))
+            for i, c in enumerate(configs):
+                ffh[i, 0:3] = LQRController._ensure_array(c.get("ff_velocity_gain", [0.0, 0.0, 0.0]))
+                ffh[i, 3:6] = LQRController._ensure_array(c.get("ff_acceleration_gain", [0.0, 0.0, 0.0]))
+            ff_gains = torch.as_tensor(ffh, **f64)
         ctx.rollout(prm, E, int(cfg.evaluation_horizon), 1, state0, tparams, K.contiguous(), proto.k_cols(),
-                    eps, metrics)
+                    eps, metrics, ff_gains=ff_gains)
         cand = torch.empty((4, C), **f64)
         ctx.reduce_scores(metrics, C, eps, cand)
         host = cand.cpu().numpy()

@@ -69,7 +69,7 @@ def np_sum(a: np.ndarray) -> float:
 
 
 def rollout(params: QtParams, state0, tparams, K, k_stride=None, max_steps=3000, chain=1,
-            ctrl_state=None, want_final_state=True, traj_stride=0, data_stride=0, n_threads=1):
+            ctrl_state=None, want_final_state=True, traj_stride=0, data_stride=0, n_threads=1, ff_gains=None):
     """Same contract as qt_rollout (include/qtrack.h).  Arrays are [F, E] float64."""
     state0, tparams, K = _f64(state0), _f64(tparams), _f64(K)
     E = state0.shape[1]
@@ -95,7 +95,7 @@ def rollout(params: QtParams, state0, tparams, K, k_stride=None, max_steps=3000,
                       _p(ctrl_state), _p(out.get("final_state")), _p(out.get("traj")),
                       C.c_int64(max(traj_stride, 1)), C.c_int64(traj_slots), _p(out.get("features")),
                       _p(out.get("actions")), C.c_int64(max(data_stride, 1)), C.c_int64(data_slots),
-                      C.c_int32(n_threads))
+                      C.c_int32(n_threads), _p(None if ff_gains is None else _f64(ff_gains)))
     return out
 
 

@@ -31,7 +31,7 @@ def reset(params, seeds, draws=None):
 
 
 def rollout(params, state0, tparams, K, k_stride=None, max_steps=3000, chain=1, ctrl_state=None,
-            want_final_state=True, traj_stride=0, data_stride=0):
+            want_final_state=True, traj_stride=0, data_stride=0, ff_gains=None):
     c = ctx()
     E = state0.shape[1]
     k_cols = k_cols_of(params)
@@ -53,7 +53,7 @@ def rollout(params, state0, tparams, K, k_stride=None, max_steps=3000, chain=1, 
     cs = dev(ctrl_state) if ctrl_state is not None else None
     c.rollout(params, E, max_steps, chain, dev(state0), dev(tparams), Kt, k_cols, k_stride, out["metrics"], cs,
               out.get("final_state"), out.get("traj"), max(traj_stride, 1), ts, out.get("features"),
-              out.get("actions"), max(data_stride, 1), dsl)
+              out.get("actions"), max(data_stride, 1), dsl, dev(ff_gains) if ff_gains is not None else None)
     res = {k: v.cpu().numpy() for k, v in out.items()}
     if cs is not None:
         ctrl_state[...] = cs.cpu().numpy()

@@ -204,3 +204,40 @@ def test_cma_es_strategy_runs_generations_as_batches_and_improves(gpu_ctx, tmp_p
                        search_space=GainSearchSpace(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]),
                                                     kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0])))
     assert ControllerTuner(pid).tune().iterations_completed == 24
+
+
+@pytest.mark.parametrize("ctype", ["pid", "riccati_lqr"])
+def test_feedforward_candidates_are_batched_and_match_single_evaluation(gpu_ctx, tmp_path, ctype):
+    """Candidates that differ in their feedforward gains share one launch (qt_rollout ff_gains); the
+    scores equal those of evaluating every candidate on its own, and the oracle's."""
+    import oracle
+    from lqr_quadcopter_test_b200 import ControllerTuner, GainSearchSpace, TuningConfig
+
+    kw = dict(ff_velocity_gain_range=([0.0, 0.0, 0.0], [0.3, 0.3, 0.1]), ff_acceleration_gain_range=([0.0, 0.0, 0.0], [0.2, 0.2, 0.05]))
+    if ctype == "pid":
+        kw.update(kp_pos_range=([0.005, 0.005, 2.0], [0.05, 0.05, 6.0]), kd_pos_range=([0.02, 0.02, 1.0], [0.15, 0.15, 3.0]))
+    else:
+        kw.update(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), r_controls_range=([0.5] * 4, [2.0] * 4))
+    tc = TuningConfig(controller_type=ctype, search_space=GainSearchSpace(**kw), strategy="random", max_iterations=6,
+                      evaluation_episodes=3, evaluation_horizon=500, seed=11, target_motion_type="circular",
+                      episode_length=5.0, output_dir=str(tmp_path))
+    tuner = ControllerTuner(tc)
+    configs = [tuner._generate_random_config() for _ in range(6)]
+    assert all(c["feedforward_enabled"] for c in configs)
+    launches0 = gpu_ctx.launches
+    scores, metrics = tuner.evaluate_configs(configs)
+    batched_launches = gpu_ctx.launches - launches0
+    singles = [tuner._evaluate_config(c) for c in configs]
+    assert batched_launches < (gpu_ctx.launches - launches0 - batched_launches) / 3
+    np.testing.assert_array_equal(scores, [s for s, _ in singles])
+    assert metrics == [m for _, m in singles]
+    # oracle: same gains, per-candidate feedforward gains
+    proto = tuner._create_controller(configs[0])
+    env, crit = tuner._env_and_criteria()
+    prm = proto.kernel_params(env, crit)
+    Ks = np.stack([np.ascontiguousarray(tuner._create_controller(c).effective_gain()) for c in configs])
+    ff = np.array([list(c["ff_velocity_gain"]) + list(c["ff_acceleration_gain"]) for c in configs])
+    s0, tp = oracle.reset_reference(prm, [11, 12, 13])
+    ref = oracle.rollout(prm, np.tile(s0, (1, 6)), np.tile(tp, (1, 6)), Ks, k_stride=3, max_steps=500, ff_gains=ff)
+    cand = oracle.reduce_scores(ref["metrics"], 6, 3)
+    np.testing.assert_allclose(scores, cand[0], rtol=0, atol=1e-10)
