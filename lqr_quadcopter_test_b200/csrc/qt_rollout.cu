@@ -44,7 +44,8 @@ struct RolloutArgs {
 // register file is what lets four 128-thread blocks (16 warps) stay resident per SM without
 // spilling.  Column access (row * blockDim + threadIdx) is conflict free.
 enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_OV_CUR, CR_OV_MAX, CR_TARGET };
-constexpr int kColdRows = CR_TARGET + QT_TARGET_PARAMS;
+constexpr int CR_TARGET_TRIG = CR_TARGET + QT_TARGET_PARAMS;  // 6 rows: carried sin/cos of the pattern angles
+constexpr int kColdRows = CR_TARGET_TRIG + 6;
 
 template <int MOTION, int CTRL, bool FULL>
 __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         int next_traj = 0, traj_slot = 0, next_data = 0, data_slot = 0;
 
         double tp[3], tv[3], ta[3];
+        tg.trig_init(cold + CR_TARGET_TRIG * T, t);
         tg.template state<FULL>(P, t, tp, tv, ta);
         double err_pre = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
         // np.max of the pre-step errors (utils/metrics.py:329).  Sample 0 initialises it; later samples are
@@ -242,7 +244,11 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 integrate<false, FAST>(C, s, actv, B, eta_old);
             constrain_state<FAST>(P, C, s);
             trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
-            t += C.dt;
+            {
+                const double t_old = t;
+                t += C.dt;
+                tg.trig_advance(t_old, t, (step & 15) == 15);
+            }
             tg.template state<FULL>(P, t, tp, tv, ta);
             {
                 const double dx = s[0] - tp[0], dy = s[1] - tp[1], dz = s[2] - tp[2];
