@@ -344,3 +344,69 @@ def test_policy_rollout_matches_oracle(golden, gb, orc, name, motion, T):
     np.testing.assert_allclose(got["actions"], ref["actions"], rtol=0, atol=gc.TOL_POLICY_STATE)
     print(f"[parity] policy {name}/{motion}: max |final state diff| = {np.abs(got['final_state'] - ref['final_state']).max():.2e}, "
           f"episodes with an on-target count differing = {(diff.max(axis=0) > 0).sum()}")
+
+
+def test_randomised_configurations_match_oracle(golden, gb, orc):
+    """Twenty random env / controller parameter sets (mass, drag, dt, limits, target pattern sizes and
+    speeds, gains, feedforward, integrator settings, all three control laws) against the oracle: the
+    flattened RK4 coefficients, the carried trig and the integer-pipe range tests all depend on these."""
+    rng = np.random.default_rng(20260101)
+    worst = 0.0
+    for trial in range(20):
+        motion = MOTIONS[trial % 5]
+        law = ("lqr", "lqi", "pid")[trial % 3]
+        env = EnvConfig()
+        env.target.motion_type = motion
+        env.quadcopter.mass = float(rng.uniform(0.6, 1.8))
+        env.quadcopter.drag_coeff_linear = float(rng.uniform(0.02, 0.4))
+        env.quadcopter.drag_coeff_angular = float(rng.uniform(0.0, 0.05))
+        env.simulation.dt = float(rng.choice([0.005, 0.01, 0.02]))
+        env.simulation.max_episode_time = float(rng.uniform(3.0, 6.0))
+        env.simulation.max_velocity = float(rng.uniform(4.0, 50.0))
+        env.simulation.max_angular_velocity = float(rng.uniform(1.0, 10.0))
+        env.simulation.max_position = float(rng.choice([6.0, 1000.0]))
+        env.target.speed = float(rng.uniform(0.3, 2.5))
+        env.target.radius = float(rng.uniform(1.0, 3.0))
+        env.target.amplitude = float(rng.uniform(0.5, 2.5))
+        env.target.frequency = float(rng.uniform(0.2, 0.9))
+        env.target.center = tuple(rng.uniform(-1.0, 2.0, 3))
+        env.success_criteria.target_radius = float(rng.uniform(0.2, 0.8))
+        ff = bool(trial % 2)
+        kw = dict(dt=env.simulation.dt, hover_thrust=env.quadcopter.mass * 9.81, max_rate=float(rng.uniform(1.5, 3.0)),
+                  feedforward_enabled=ff, ff_velocity_gain=list(rng.uniform(0, 0.3, 3)),
+                  ff_acceleration_gain=list(rng.uniform(0, 0.2, 3)), ff_max_velocity=float(rng.uniform(0.5, 3.0)),
+                  ff_max_acceleration=float(rng.uniform(0.3, 3.0)))
+        if law == "pid":
+            kw.update(name="pid", integral_limit=float(rng.choice([0.0, 0.3])))
+            K = np.array([[0.01, 0.01, 4.0], [0.003, 0.003, 0.4], [0.06, 0.06, 2.0], [0, 0, 0]]) * rng.uniform(0.5, 1.5, (4, 3))
+        elif law == "lqi":
+            kw.update(use_lqi=True, integral_limit=float(rng.uniform(0.05, 2.0)), integral_zero_threshold=float(rng.uniform(0.0, 0.1)))
+            K = _axis_decoupled(golden["dare"]["lqi_default_K"]) * rng.uniform(0.6, 1.2, (4, 9))
+            K[:, 6:] *= 0.05     # a mild integral gain: the reference's default one diverges
+            if trial % 4 == 1:
+                K = K + rng.standard_normal((4, 9)) * 1e-3    # dense gain: the general loop
+        else:
+            K = _axis_decoupled(golden["dare"]["lqr_default_K"]) * rng.uniform(0.6, 1.4, (4, 6))
+            if trial % 4 == 0:
+                K = K + rng.standard_normal((4, 6)) * 1e-3
+        crit = type("C", (), dict(target_radius=env.success_criteria.target_radius, min_on_target_ratio=0.5,
+                                   min_episode_duration=env.simulation.max_episode_time))()
+        prm = P.make_params(env, gc.controller_ns(**kw), crit)
+        E = 96
+        s0, tp = orc.reset_reference(prm, np.arange(5000 + 100 * trial, 5000 + 100 * trial + E))
+        if trial % 5 == 3:
+            s0[8] = rng.uniform(-0.5, 0.5, E)     # non-zero yaw: general loop
+        steps = int(np.ceil(env.simulation.max_episode_time / env.simulation.dt)) + 2
+        ref = orc.rollout(prm, s0, tp, K, max_steps=steps, n_threads=8, traj_stride=97)
+        got = gb.rollout(prm, s0, tp, K, max_steps=steps, traj_stride=97)
+        # figure-8 + feedforward: the reference's target acceleration is a finite difference with h = 1e-6
+        # (target_motion.py:209-229) that amplifies a 1-ulp sin/cos difference to ~1e-4, and feedforward
+        # feeds it into the action - two libm builds of the reference itself would differ as much
+        noisy = motion == "figure8" and ff
+        tol = 2e-4 if noisy else 1e-9
+        label = f"trial {trial} {law}/{motion} ff={ff}"
+        _compare_rollouts(got, ref, tol, label)
+        np.testing.assert_allclose(got["traj"], ref["traj"], rtol=0, atol=5e-3 if noisy else tol, err_msg=label)
+        if not noisy:
+            worst = max(worst, float(np.abs(got["final_state"] - ref["final_state"]).max()))
+    print(f"[parity] 20 randomised configurations: max |final state diff| = {worst:.2e} (figure-8 + feedforward excluded)")
