@@ -15,7 +15,7 @@ from .controller import (ACTION_KEYS, BaseController, LQRController, PIDControll
 from .env import BatchedQuadcopterEnv, QuadcopterEnv
 from .policy import DeepTrackingPolicy, create_controller_from_config, make_policy_network
 from .train import Trainer, TrainingConfig, load_checkpoint_and_resume
-from .eval import Evaluator, load_controller, rollout_device
+from .eval import Evaluator, load_controller, rollout_device, run_hyperparameter_sweep
 from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, format_metrics_report)
 from .tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
 from .dataset import teacher_dataset
@@ -27,7 +27,7 @@ __all__ = [
     "EnvSuccessCriteria", "SuccessCriteria", "QuadcopterEnv", "BatchedQuadcopterEnv",
     "RiccatiLQRController", "LQRController", "PIDController", "DeepTrackingPolicy",
     "create_controller_from_config", "make_policy_network", "Trainer", "TrainingConfig",
-    "load_checkpoint_and_resume", "BaseController", "ACTION_KEYS", "solve_dare",
+    "load_checkpoint_and_resume", "run_hyperparameter_sweep", "BaseController", "ACTION_KEYS", "solve_dare",
     "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
     "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
     "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",

@@ -307,3 +307,46 @@ def load_controller(controller_type: str, checkpoint_path: str | Path | None = N
             controller.load_checkpoint(checkpoint_path)
         return controller
     raise ValueError(f"Unknown controller type: {controller_type}")
+
+
+def run_hyperparameter_sweep(sweep_config_path: str | Path, output_dir: str | Path = "reports/sweeps") -> list[dict]:
+    """eval.py:516-628: evaluate every entry of a sweep YAML/JSON (``configurations: [{name, controller_type,
+    controller_config, checkpoint_path, env_config, criteria, num_episodes, seed}, ...]``) and rank the
+    results by mean on-target ratio.  Each configuration is one fused launch over its episodes."""
+    path = Path(sweep_config_path)
+    with open(path) as f:
+        if path.suffix == ".json":
+            sweep_config = json.load(f)
+        else:
+            import yaml
+
+            sweep_config = yaml.safe_load(f)
+    output_dir = Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    results = []
+    for i, config in enumerate((sweep_config or {}).get("configurations", [])):
+        name = config.get("name", f"config_{i}")
+        try:
+            controller = load_controller(controller_type=config.get("controller_type", "deep"),
+                                         checkpoint_path=config.get("checkpoint_path"),
+                                         config=config.get("controller_config"))
+            env_config = EnvConfig.from_dict(config["env_config"]) if "env_config" in config else EnvConfig()
+            crit = config.get("criteria", {})
+            criteria = SuccessCriteria(min_on_target_ratio=crit.get("min_on_target_ratio", 0.8),
+                                       min_episode_duration=crit.get("min_episode_duration", 30.0),
+                                       target_radius=crit.get("target_radius", 0.5))
+            evaluator = Evaluator(controller=controller, env_config=env_config, criteria=criteria,
+                                  output_dir=output_dir / name)
+            summary = evaluator.evaluate(num_episodes=config.get("num_episodes", 5), base_seed=config.get("seed", 42),
+                                         verbose=False)
+            results.append({"name": name, "config": config, "mean_on_target_ratio": summary.mean_on_target_ratio,
+                            "success_rate": summary.success_rate, "mean_tracking_error": summary.mean_tracking_error,
+                            "meets_criteria": summary.meets_criteria})
+        except Exception as e:  # the reference records the failure and carries on (eval.py:590-598)
+            logger.error("Configuration %s failed: %s", name, e)
+            results.append({"name": name, "config": config, "error": str(e)})
+    valid = [r for r in results if "error" not in r]
+    valid.sort(key=lambda r: r["mean_on_target_ratio"], reverse=True)
+    with open(output_dir / "sweep_results.json", "w") as f:
+        json.dump(valid, f, indent=2)
+    return valid

@@ -241,3 +241,25 @@ def test_feedforward_candidates_are_batched_and_match_single_evaluation(gpu_ctx,
     ref = oracle.rollout(prm, np.tile(s0, (1, 6)), np.tile(tp, (1, 6)), Ks, k_stride=3, max_steps=500, ff_gains=ff)
     cand = oracle.reduce_scores(ref["metrics"], 6, 3)
     np.testing.assert_allclose(scores, cand[0], rtol=0, atol=1e-10)
+
+
+def test_hyperparameter_sweep_ranks_configurations(gpu_ctx, tmp_path):
+    """eval.py:516-628: sweep file -> ranked results; a broken entry is recorded and skipped."""
+    import json
+
+    from lqr_quadcopter_test_b200 import run_hyperparameter_sweep
+
+    sweep = {"configurations": [
+        {"name": "pid", "controller_type": "pid", "num_episodes": 4, "seed": 42,
+         "env_config": {"target": {"motion_type": "linear"}}},
+        {"name": "riccati", "controller_type": "riccati_lqr", "num_episodes": 4, "seed": 42,
+         "env_config": {"target": {"motion_type": "linear"}}, "criteria": {"min_on_target_ratio": 0.5}},
+        {"name": "broken", "controller_type": "no_such_controller"},
+    ]}
+    path = tmp_path / "sweep.json"
+    path.write_text(json.dumps(sweep))
+    ranked = run_hyperparameter_sweep(path, tmp_path / "out")
+    assert [r["name"] for r in ranked] == ["riccati", "pid"]            # better on-target ratio first
+    assert ranked[0]["mean_on_target_ratio"] > ranked[1]["mean_on_target_ratio"]
+    saved = json.loads((tmp_path / "out" / "sweep_results.json").read_text())
+    assert [r["name"] for r in saved] == ["riccati", "pid"]
