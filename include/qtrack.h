@@ -64,6 +64,9 @@ enum qt_controller { QT_CTRL_RICCATI = 0, QT_CTRL_PID = 1 };
 /* qt_params.debug_flags.  QT_DEBUG_GENERAL_PATH: qt_rollout always runs the general step loop, never
  * the structure-exploiting one (zero yaw, axis-decoupled gain); results must not change (tests).  */
 #define QT_DEBUG_GENERAL_PATH 1
+/* QT_DEBUG_POLICY_PER_THREAD: qt_rollout_policy evaluates the network one episode per thread even where
+ * the warp-cooperative tiled evaluation applies; results must not change (tests).                   */
+#define QT_DEBUG_POLICY_PER_THREAD 2
 
 /* quadcopter_env.py:513-535; 0 = the step cap ended the loop, not the environment */
 enum qt_termination {

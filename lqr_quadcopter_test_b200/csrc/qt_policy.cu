@@ -32,6 +32,14 @@ struct MlpDesc {
     int tile_w[2];                   // widths (floats per thread) of the two activation tiles: hidden layer l
                                      // (0-based) is stored in tile l & 1; the last hidden layer is not stored
     float out_lo[4], out_scale[4];
+    // TILED evaluation: hidden widths padded to multiples of 64 (zero weights and biases, so a padded unit
+    // outputs activation(0) = 0 and feeds zero rows of the next layer)
+    int tiled;                       // 1 if the tiled evaluation applies to this shape
+    int t_rows[QT_MLP_MAX_LAYERS];   // input rows of layer l in the staged (tiled) layout
+    int t_n[QT_MLP_MAX_LAYERS];      // output width of layer l in the staged layout (last layer: 4)
+    int t_off[QT_MLP_MAX_LAYERS];    // offset (floats) of Wt of layer l in the staged layout; bias follows
+    int t_total;                     // floats of the staged weights
+    int t_buf[2];                    // rows (of 32 floats) of the two per-warp activation buffers
 };
 
 static bool describe(const qt_mlp &m, MlpDesc &d) {
@@ -55,6 +63,23 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
         d.out_lo[i] = m.out_lo[i];
         d.out_scale[i] = m.out_scale[i];
     }
+    // tiled layout: layer l reads activation buffer l & 1 and writes buffer (l + 1) & 1; the features are in buffer 0
+    int toff = 0;
+    long fma_tiled = 0, fma_packed = 0;
+    d.t_buf[0] = QT_FEATURE_DIM;
+    d.t_buf[1] = 0;
+    for (int l = 0; l < m.n_layers; l++) {
+        const bool last = l == m.n_layers - 1;
+        d.t_rows[l] = l == 0 ? QT_FEATURE_DIM : d.t_n[l - 1];
+        d.t_n[l] = last ? 4 : ((m.dims[l + 1] + 63) & ~63);
+        d.t_off[l] = toff;
+        toff += d.t_rows[l] * d.t_n[l] + d.t_n[l];
+        if (!last && d.t_n[l] > d.t_buf[(l + 1) & 1]) d.t_buf[(l + 1) & 1] = d.t_n[l];
+        fma_tiled += (long)d.t_rows[l] * d.t_n[l];
+        fma_packed += (long)d.rows[l] * d.outp[l];
+    }
+    d.t_total = (toff + 3) & ~3;
+    d.tiled = m.n_layers >= 2 && fma_tiled * 4 <= fma_packed * 5;   // at most 25 % padding work
     return true;
 }
 
@@ -186,6 +211,123 @@ __device__ __forceinline__ void mlp_forward(const MlpDesc &M, const float *__res
     }
 }
 
+// ---- TILED evaluation ----------------------------------------------------------------------------
+// A warp's 32 episodes x the N units of a layer is a small GEMM.  Lane (er, jc) = (lane / 8, lane % 8)
+// owns episodes {4 er .. 4 er + 3, 16 + 4 er .. 16 + 4 er + 3} and, of every 64-unit column tile, units
+// {4 jc .. 4 jc + 3, 32 + 4 jc .. 32 + 4 jc + 3}: 64 accumulators.  One k-step loads two float4 of
+// activations and two float4 of weights and issues 64 FFMAs (the per-thread evaluation needs one
+// float4 of weights per 4 FFMAs and is bound by the shared-memory pipe and its latency).  Every
+// accumulator starts from its bias and adds x_k * w_kj in ascending k, exactly as the per-thread
+// evaluation does, so the two give identical bits.
+// Activation buffers are per warp, [unit][episode] with 32 floats per unit; the 16-byte chunk c of
+// row j is stored at chunk c ^ ((j >> 2) & 7), which makes the transposed float4 stores of the
+// epilogue, the float4 loads of the k-loop and the per-episode scalar accesses all conflict free.
+__device__ __forceinline__ int tile_elem(int row, int lane) {   // float index of (unit row, episode lane)
+    return row * 32 + ((((lane >> 2) ^ (row >> 2)) & 7) << 2) + (lane & 3);
+}
+
+template <int KIND>
+__device__ __forceinline__ void tile_layer(const float *__restrict__ Wt, const float *__restrict__ bias, int K, int N,
+                                           const float *xin, float *xout, int er, int jc) {
+    for (int j0 = 0; j0 < N; j0 += 64) {
+        float acc[8][8];
+        {
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + j0 + jc * 4);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias + j0 + 32 + jc * 4);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+                acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+            }
+        }
+        const float *wp = Wt + j0 + jc * 4;
+#pragma unroll 2
+        for (int k = 0; k < K; k++) {
+            const int sw = (k >> 2) & 7;
+            const float4 a0 = *reinterpret_cast<const float4 *>(xin + k * 32 + ((er ^ sw) << 2));
+            const float4 a1 = *reinterpret_cast<const float4 *>(xin + k * 32 + (((4 + er) ^ sw) << 2));
+            const float4 w0 = *reinterpret_cast<const float4 *>(wp + (size_t)k * N);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wp + (size_t)k * N + 32);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
+        }
+        const int sw = ((j0 >> 2) + jc) & 7;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int j = j0 + (c < 4 ? jc * 4 + c : 32 + jc * 4 + (c - 4));
+            float *row = xout + j * 32;
+            *reinterpret_cast<float4 *>(row + ((er ^ sw) << 2)) =
+                make_float4(activate_t<KIND>(acc[0][c]), activate_t<KIND>(acc[1][c]), activate_t<KIND>(acc[2][c]),
+                            activate_t<KIND>(acc[3][c]));
+            *reinterpret_cast<float4 *>(row + (((4 + er) ^ sw) << 2)) =
+                make_float4(activate_t<KIND>(acc[4][c]), activate_t<KIND>(acc[5][c]), activate_t<KIND>(acc[6][c]),
+                            activate_t<KIND>(acc[7][c]));
+        }
+    }
+}
+
+// PolicyNetwork.forward for the 32 feature vectors of a warp (one per lane); every lane of the warp must
+// call it.  W: staged tiled weights (shared memory); buf0 / buf1: this warp's activation buffers.
+__device__ __forceinline__ void mlp_forward_tiled(const MlpDesc &M, const float *__restrict__ W, float *buf0, float *buf1,
+                                                  const float (&feat)[QT_FEATURE_DIM], float (&out)[4]) {
+    const int lane = threadIdx.x & 31, er = lane >> 3, jc = lane & 7;
+    const int L = M.n_layers;
+    __syncwarp();   // the previous evaluation's output layer has finished reading the buffers
+#pragma unroll
+    for (int k = 0; k < QT_FEATURE_DIM; k++) buf0[tile_elem(k, lane)] = feat[k];
+    __syncwarp();
+    for (int l = 0; l + 1 < L; l++) {
+        const float *Wt = W + M.t_off[l];
+        const int K = M.t_rows[l], N = M.t_n[l];
+        const float *xin = (l & 1) ? buf1 : buf0;
+        float *xout = (l & 1) ? buf0 : buf1;
+        switch (M.activation) {
+        case QT_ACT_TANH: tile_layer<QT_ACT_TANH>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
+        case QT_ACT_ELU: tile_layer<QT_ACT_ELU>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
+        case QT_ACT_LEAKY_RELU: tile_layer<QT_ACT_LEAKY_RELU>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
+        default: tile_layer<QT_ACT_RELU>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
+        }
+        __syncwarp();
+    }
+    // output layer: four units, evaluated by each lane for its own episode
+    const float *xin = ((L - 1) & 1) ? buf1 : buf0;
+    const float *Wo = W + M.t_off[L - 1];
+    const int rows_o = M.t_rows[L - 1];
+    float o[4];
+    chunk_bias<4>(Wo + rows_o * 4, 0, o);
+#pragma unroll 4
+    for (int k = 0; k < rows_o; k++) chunk_fma<4>(Wo + k * 4, xin[tile_elem(k, lane)], o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float sg = 1.0f / (1.0f + expf(-o[i]));  // torch.sigmoid
+        out[i] = fmaf(sg, M.out_scale[i], M.out_lo[i]);
+    }
+}
+
+// Stage the packed weights (global) into the tiled layout at the start of shared memory.
+__device__ __forceinline__ void stage_weights_tiled(const MlpDesc &M, const float *__restrict__ Wg, float *smem_w) {
+    for (int l = 0; l < M.n_layers; l++) {
+        const int K = M.t_rows[l], N = M.t_n[l], rows = M.rows[l];
+        const int outp = M.outp[l];
+        const float *src = Wg + M.w_off[l];
+        float *dst = smem_w + M.t_off[l];
+        for (int i = threadIdx.x; i < K * N + N; i += blockDim.x) {
+            const int k = i / N, j = i - k * N;
+            float v = 0.0f;
+            if (j < outp) {
+                if (k < rows) v = src[k * outp + j];
+                else if (k == K) v = src[rows * outp + j];   // the bias row
+            }
+            dst[i] = v;
+        }
+    }
+    __syncthreads();
+}
+
 // deep_tracking_policy.py:241-286: fp64 differences first, then the fp32 cast
 __device__ __forceinline__ void make_features(const double (&s)[12], const double (&tp)[3], const double (&tv)[3],
                                               float (&x)[QT_FEATURE_DIM]) {
@@ -218,23 +360,36 @@ __device__ __forceinline__ void stage_weights(const MlpDesc &M, const float *Wg,
     __syncthreads();
 }
 
-// MINB = resident blocks per SM the register allocator must allow.  Measured (2^18 episodes): with the
-// weights in shared memory three blocks of 168 registers beat two of 255 (64-64 network 2.40e9 against
-// 2.19e9 env-steps/s); when the weights are too large to stage and stream from L1/L2 instead, the deeper
-// load prefetch that 255 registers allow wins (128-128: 4.0e8 against 2.4e8).
-template <int MOTION, int MINB>
+// MINB = resident blocks per SM the register allocator must allow.  Measured (2^18 episodes), per-thread
+// evaluation: with the weights in shared memory three blocks of 168 registers beat two of 255 (64-64
+// network 2.40e9 against 2.19e9 env-steps/s); when the weights are too large to stage and stream from
+// L1/L2 instead, the deeper load prefetch that 255 registers allow wins (128-128: 4.0e8 against 2.4e8).
+// TILED: the warp-cooperative evaluation (64 accumulators per lane, two blocks per SM).
+template <int MOTION, int MINB, bool TILED>
 __global__ void __launch_bounds__(kPolicyThreads, MINB)
     rollout_policy_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                           const __grid_constant__ MlpDesc M, const __grid_constant__ PolicyArgs A) {
     extern __shared__ __align__(16) float smem_f[];
     constexpr int T = kPolicyThreads;
     const int64_t E = A.E;
-    const int64_t e = (int64_t)blockIdx.x * T + threadIdx.x;
-    const int w_floats = A.w_in_smem ? ((M.total_floats + 3) & ~3) : 0;
-    stage_weights(M, A.W, A.w_in_smem, smem_f);
-    float *tile0 = smem_f + w_floats + threadIdx.x;
-    float *tile1 = tile0 + M.tile_w[0] * T;
-    if (e >= E) return;
+    const int64_t e_raw = (int64_t)blockIdx.x * T + threadIdx.x;
+    float *tile0, *tile1;
+    if constexpr (TILED) {
+        stage_weights_tiled(M, A.W, smem_f);
+        float *wb = smem_f + M.t_total + (threadIdx.x >> 5) * (M.t_buf[0] + M.t_buf[1]) * 32;
+        tile0 = wb;
+        tile1 = wb + M.t_buf[0] * 32;
+    } else {
+        const int w_floats = A.w_in_smem ? ((M.total_floats + 3) & ~3) : 0;
+        stage_weights(M, A.W, A.w_in_smem, smem_f);
+        tile0 = smem_f + w_floats + threadIdx.x;
+        tile1 = tile0 + M.tile_w[0] * T;
+        if (e_raw >= E) return;
+    }
+    // TILED: the lanes past the last episode stay, because the whole warp evaluates the network together;
+    // they shadow the last episode and never write
+    const bool valid = e_raw < E;
+    const int64_t e = valid ? e_raw : E - 1;
 
     double s[12];
 #pragma unroll
@@ -262,21 +417,30 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
     tg.template state<true>(P, t, tp, tv, ta);
     double err_pre = norm3d(tp[0] - s[0], tp[1] - s[1], tp[2] - s[2]);
 
-    while (term == QT_TERM_NONE && step < A.max_steps) {
+    bool alive = valid && A.max_steps > 0;
+    while (true) {
+        if constexpr (TILED) {
+            if (!__any_sync(0xffffffffu, alive)) break;
+        } else {
+            if (!alive) break;
+        }
         // ---- the policy acts on the pre-step observation
         float feat[QT_FEATURE_DIM];
         make_features(s, tp, tv, feat);
-        const bool log_data = A.feat && step == next_data && data_slot < A.data_slots;
+        const bool log_data = alive && A.feat && step == next_data && data_slot < A.data_slots;
         if (log_data) {
             float *f = A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM;
 #pragma unroll
             for (int i = 0; i < QT_FEATURE_DIM; i += 2) *reinterpret_cast<float2 *>(f + i) = make_float2(feat[i], feat[i + 1]);
         }
         float out[4];
-        if (A.w_in_smem)   // two inlined copies: one reads the weights with LDS, the other with LDG
+        if constexpr (TILED)
+            mlp_forward_tiled(M, smem_f, tile0, tile1, feat, out);
+        else if (A.w_in_smem)   // two inlined copies: one reads the weights with LDS, the other with LDG
             mlp_forward<T>(M, smem_f, tile0, tile1, feat, out);
         else
             mlp_forward<T>(M, A.W, tile0, tile1, feat, out);
+        if (!alive) continue;   // TILED only: this lane's episode is over, it only helps the warp
         double act[4] = {(double)out[0], (double)out[1], (double)out[2], (double)out[3]};
 
         // ---- supervisor label on the same observation (train.py:682-696)
@@ -363,7 +527,9 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
         }
         step += 1;
         err_pre = err_post;
+        alive = term == QT_TERM_NONE && step < A.max_steps;
     }
+    if (!valid) return;
     if (in_phase && streak >= P.overshoot_window) {
         ov_count += 1;
         ov_max = fmax(ov_max, ov_cur);
@@ -434,7 +600,7 @@ __global__ void __launch_bounds__(kPolicyThreads)
     for (int i = 0; i < 4; i++) A.action[(int64_t)i * E + e] = (double)out[i];
 }
 
-// shared memory plan: [weights if they fit][activation tile 0][activation tile 1]
+// shared memory plan, per-thread evaluation: [weights if they fit][activation tile 0][activation tile 1]
 static size_t smem_plan(const MlpDesc &M, int &w_in_smem) {
     const size_t act = (size_t)(M.tile_w[0] + M.tile_w[1]) * kPolicyThreads * sizeof(float);
     const size_t w = (((size_t)M.total_floats + 3) & ~(size_t)3) * sizeof(float);
@@ -443,21 +609,36 @@ static size_t smem_plan(const MlpDesc &M, int &w_in_smem) {
     return act + (w_in_smem ? w : 0);
 }
 
+// tiled evaluation: [staged weights][per warp: buffer 0, buffer 1]
+static size_t smem_plan_tiled(const MlpDesc &M) {
+    return ((size_t)M.t_total + (size_t)(kPolicyThreads / 32) * (M.t_buf[0] + M.t_buf[1]) * 32) * sizeof(float);
+}
+
+template <int MOTION, int MINB, bool TILED>
+static cudaError_t launch_policy_as(const qt_params &P, const DynConsts &C, const MlpDesc &M, const PolicyArgs &A,
+                                    size_t smem, cudaStream_t st) {
+    const int64_t blocks = (A.E + kPolicyThreads - 1) / kPolicyThreads;
+    cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, MINB, TILED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rollout_policy_kernel<MOTION, MINB, TILED><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    return cudaGetLastError();
+}
+
 template <int MOTION>
-static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, const PolicyArgs &A, size_t smem, cudaStream_t st) {
+static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, PolicyArgs &A, cudaStream_t st, bool &too_wide) {
     DynConsts C;
     C.init(P);
-    const int64_t blocks = (A.E + kPolicyThreads - 1) / kPolicyThreads;
-    if (A.w_in_smem && smem <= 72 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        rollout_policy_kernel<MOTION, 3><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        rollout_policy_kernel<MOTION, 2><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    too_wide = false;
+    if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024)
+        return launch_policy_as<MOTION, 2, true>(P, C, M, A, smem_plan_tiled(M), st);
+    const size_t smem = smem_plan(M, A.w_in_smem);
+    if (smem > 200 * 1024) {
+        too_wide = true;
+        return cudaSuccess;
     }
-    return cudaGetLastError();
+    if (A.w_in_smem && smem <= 72 * 1024) return launch_policy_as<MOTION, 3, false>(P, C, M, A, smem, st);
+    return launch_policy_as<MOTION, 2, false>(P, C, M, A, smem, st);
 }
 
 }  // namespace qt
@@ -531,17 +712,18 @@ extern "C" int qt_rollout_policy(qt_context *ctx, const qt_params *params, int64
     A.traj_slots = (int)traj_slots;
     A.data_stride = (int)data_stride;
     A.data_slots = (int)data_slots;
-    const size_t smem = smem_plan(M, A.w_in_smem);
-    QT_REQUIRE(ctx, smem <= 200 * 1024, "network too wide for the shared-memory activation tiles");
+    A.w_in_smem = 0;
     DeviceGuard guard(ctx->device);
     cudaError_t err;
+    bool too_wide = false;
     switch (params->motion_type) {
-    case QT_MOTION_LINEAR: err = launch_policy<QT_MOTION_LINEAR>(*params, M, A, smem, ctx->stream); break;
-    case QT_MOTION_CIRCULAR: err = launch_policy<QT_MOTION_CIRCULAR>(*params, M, A, smem, ctx->stream); break;
-    case QT_MOTION_SINUSOIDAL: err = launch_policy<QT_MOTION_SINUSOIDAL>(*params, M, A, smem, ctx->stream); break;
-    case QT_MOTION_FIGURE8: err = launch_policy<QT_MOTION_FIGURE8>(*params, M, A, smem, ctx->stream); break;
-    default: err = launch_policy<QT_MOTION_STATIONARY>(*params, M, A, smem, ctx->stream); break;
+    case QT_MOTION_LINEAR: err = launch_policy<QT_MOTION_LINEAR>(*params, M, A, ctx->stream, too_wide); break;
+    case QT_MOTION_CIRCULAR: err = launch_policy<QT_MOTION_CIRCULAR>(*params, M, A, ctx->stream, too_wide); break;
+    case QT_MOTION_SINUSOIDAL: err = launch_policy<QT_MOTION_SINUSOIDAL>(*params, M, A, ctx->stream, too_wide); break;
+    case QT_MOTION_FIGURE8: err = launch_policy<QT_MOTION_FIGURE8>(*params, M, A, ctx->stream, too_wide); break;
+    default: err = launch_policy<QT_MOTION_STATIONARY>(*params, M, A, ctx->stream, too_wide); break;
     }
+    QT_REQUIRE(ctx, !too_wide, "network too wide for the shared-memory activation tiles");
     if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "rollout_policy_kernel launch", cudaGetErrorString(err));
     ctx->launches += 1;
     return QT_OK;

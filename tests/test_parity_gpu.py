@@ -346,6 +346,40 @@ def test_policy_rollout_matches_oracle(golden, gb, orc, name, motion, T):
           f"episodes with an on-target count differing = {(diff.max(axis=0) > 0).sum()}")
 
 
+@pytest.mark.parametrize("hidden,act,motion", [([64, 64], "relu", "linear"), ([64], "tanh", "circular"),
+                                               ([128, 64], "elu", "sinusoidal"), ([64, 64, 64], "leaky_relu", "figure8"),
+                                               ([60, 120], "relu", "stationary")])
+def test_tiled_policy_evaluation_is_identical_to_per_thread(golden, gb, orc, hidden, act, motion):
+    """qt_rollout_policy's warp-cooperative (tiled) network evaluation against the one-episode-per-thread
+    evaluation forced through qt_params.debug_flags: same sums in the same order, so every output must have
+    the same bits.  1000 episodes (a partial last warp), random networks (episodes leave the box and end at
+    different steps, so warps run with finished lanes), supervisor labels and both logs on."""
+    import copy
+
+    import torch
+
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy
+
+    torch.manual_seed(len(hidden) * 1000 + hidden[0])
+    pol = DeepTrackingPolicy(config={"hidden_sizes": hidden, "activation": act})
+    E = 1000
+    env = EnvConfig()
+    env.target.motion_type = motion
+    env.simulation.max_position = 30.0   # random networks drift away: episodes end at different steps
+    prm = P.make_params(env, gc.controller_ns())
+    per_thread = copy.copy(prm)
+    per_thread.debug_flags = 2
+    s0, tp = orc.reset_reference(prm, np.arange(300, 300 + E))
+    K = golden["dare"]["lqr_default_K"]
+    a = gb.rollout_policy(prm, s0, tp, pol, K=K, max_steps=1200, data_stride=7, traj_stride=50)
+    b = gb.rollout_policy(per_thread, s0, tp, pol, K=K, max_steps=1200, data_stride=7, traj_stride=50)
+    for key in a:
+        np.testing.assert_array_equal(a[key], b[key], err_msg=f"{hidden}/{act}/{motion}: {key}")
+    steps = a["metrics"][P.M_STEPS]
+    print(f"[parity] tiled policy {hidden}/{act}/{motion}: episode lengths {int(steps.min())}..{int(steps.max())}, "
+          f"{int((steps < 1200).sum())} of {E} ended early")
+
+
 def test_randomised_configurations_match_oracle(golden, gb, orc):
     """Twenty random env / controller parameter sets (mass, drag, dt, limits, target pattern sizes and
     speeds, gains, feedforward, integrator settings, all three control laws) against the oracle: the
