@@ -19,6 +19,9 @@
 namespace qt {
 
 constexpr int kPolicyThreads = 128;
+#ifndef QT_POLICY_TILED_3
+#define QT_POLICY_TILED_3 1
+#endif
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
@@ -40,6 +43,7 @@ struct MlpDesc {
     int t_off[QT_MLP_MAX_LAYERS];    // offset (floats) of Wt of layer l in the staged layout; bias follows
     int t_total;                     // floats of the staged weights
     int t_buf[2];                    // rows (of 32 floats) of the two per-warp activation buffers
+    int t_inplace;                   // every hidden layer is one 64-unit column tile: the layers run in place in buffer 0
 };
 
 static bool describe(const qt_mlp &m, MlpDesc &d) {
@@ -79,6 +83,14 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
         fma_packed += (long)d.rows[l] * d.outp[l];
     }
     d.t_total = (toff + 3) & ~3;
+    d.t_inplace = 1;
+    for (int l = 0; l + 1 < m.n_layers; l++) d.t_inplace &= d.t_n[l] == 64;
+    if (d.t_inplace) {   // a layer's outputs are complete in registers before the first of them is stored
+        d.t_buf[0] = 64;
+        d.t_buf[1] = 0;
+    }
+    d.t_buf[0] += 2;     // tile_layer's operand prefetch runs two rows past the layer's input
+    if (d.t_buf[1]) d.t_buf[1] += 2;
     d.tiled = m.n_layers >= 2 && fma_tiled * 4 <= fma_packed * 5;   // at most 25 % padding work
     return true;
 }
@@ -226,46 +238,105 @@ __device__ __forceinline__ int tile_elem(int row, int lane) {   // float index o
     return row * 32 + ((((lane >> 2) ^ (row >> 2)) & 7) << 2) + (lane & 3);
 }
 
+// Two fp32 FMAs in one instruction (sm_100 FFMA2): acc.lo += a * w.lo, acc.hi += a * w.hi, each rounded
+// exactly like fmaf.  The FP32 pipe does the same work either way; what halves is the number of issue
+// slots the 5 504 FMAs of a 64-64 network take, and the tiled kernel is issue-bound.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(float a, unsigned long long w, unsigned long long &acc) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(a, a)), "l"(w));   // in place: no accumulator copies
+}
+
 template <int KIND>
 __device__ __forceinline__ void tile_layer(const float *__restrict__ Wt, const float *__restrict__ bias, int K, int N,
                                            const float *xin, float *xout, int er, int jc) {
+    const bool inplace = xin == xout;   // only with a single column tile (MlpDesc::t_inplace)
     for (int j0 = 0; j0 < N; j0 += 64) {
-        float acc[8][8];
+        unsigned long long acc[8][4];   // [episode][unit pair]
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(bias + j0 + jc * 4);
             const float4 b1 = *reinterpret_cast<const float4 *>(bias + j0 + 32 + jc * 4);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
-                acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
-            }
-        }
-        const float *wp = Wt + j0 + jc * 4;
-#pragma unroll 2
-        for (int k = 0; k < K; k++) {
-            const int sw = (k >> 2) & 7;
-            const float4 a0 = *reinterpret_cast<const float4 *>(xin + k * 32 + ((er ^ sw) << 2));
-            const float4 a1 = *reinterpret_cast<const float4 *>(xin + k * 32 + (((4 + er) ^ sw) << 2));
-            const float4 w0 = *reinterpret_cast<const float4 *>(wp + (size_t)k * N);
-            const float4 w1 = *reinterpret_cast<const float4 *>(wp + (size_t)k * N + 32);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const unsigned long long b[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
-                for (int c = 0; c < 8; c++) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
+                for (int c = 0; c < 4; c++) acc[i][c] = b[c];
         }
+        const float *wp = Wt + j0 + jc * 4;
+        // Software pipeline: two operand sets (A, B), each reloaded in place right after its last use, so
+        // the loads of step k + 2 fly during the 32 FFMA2 of step k + 1.  Rows are walked in groups of
+        // four (one swizzle per group) plus a tail of two (K is 18 or a multiple of 64).
+        struct Operands {
+            float4 a0, a1, w0, w1;
+        };
+        auto load = [&](const float *xr, const float *wr, int o0, int o1, Operands &v) {
+            v.a0 = *reinterpret_cast<const float4 *>(xr + o0);
+            v.a1 = *reinterpret_cast<const float4 *>(xr + o1);
+            v.w0 = *reinterpret_cast<const float4 *>(wr);
+            v.w1 = *reinterpret_cast<const float4 *>(wr + 32);
+        };
+        auto fma_all = [&](const Operands &v) {
+            const float a[8] = {v.a0.x, v.a0.y, v.a0.z, v.a0.w, v.a1.x, v.a1.y, v.a1.z, v.a1.w};
+            const unsigned long long w[4] = {pack2(v.w0.x, v.w0.y), pack2(v.w0.z, v.w0.w), pack2(v.w1.x, v.w1.y),
+                                             pack2(v.w1.z, v.w1.w)};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) ffma2(a[i], w[c], acc[i][c]);
+        };
+        const int G = K >> 2;
+        const bool tail = (K & 3) != 0;
+        const float *xr = xin, *wr = wp;     // first row of the current group
+        int o0 = er << 2, o1 = (4 + er) << 2;  // swizzled chunk offsets of the current group
+        Operands A, B;
+        load(xr, wr, o0, o1, A);
+        load(xr + 32, wr + N, o0, o1, B);
+#pragma unroll 1
+        for (int g = 0; g < G; g++) {
+            fma_all(A);
+            load(xr + 64, wr + 2 * N, o0, o1, A);
+            fma_all(B);
+            load(xr + 96, wr + 3 * N, o0, o1, B);
+            // after the last group these loads fetch rows K and K + 1, which exist (two spare rows per
+            // activation buffer; the bias row and the next layer follow the weights) and are not used
+            xr += 128;
+            wr += 4 * N;
+            const int sw = (g + 1) & 7;
+            o0 = (er ^ sw) << 2;
+            o1 = ((4 + er) ^ sw) << 2;
+            fma_all(A);
+            load(xr, wr, o0, o1, A);
+            fma_all(B);
+            load(xr + 32, wr + N, o0, o1, B);
+        }
+        if (tail) {
+            fma_all(A);
+            fma_all(B);
+        }
+        if (inplace) __syncwarp();   // every lane has read the inputs it needs
         const int sw = ((j0 >> 2) + jc) & 7;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int j = j0 + (c < 4 ? jc * 4 + c : 32 + jc * 4 + (c - 4));
-            float *row = xout + j * 32;
-            *reinterpret_cast<float4 *>(row + ((er ^ sw) << 2)) =
-                make_float4(activate_t<KIND>(acc[0][c]), activate_t<KIND>(acc[1][c]), activate_t<KIND>(acc[2][c]),
-                            activate_t<KIND>(acc[3][c]));
-            *reinterpret_cast<float4 *>(row + (((4 + er) ^ sw) << 2)) =
-                make_float4(activate_t<KIND>(acc[4][c]), activate_t<KIND>(acc[5][c]), activate_t<KIND>(acc[6][c]),
-                            activate_t<KIND>(acc[7][c]));
+        for (int c = 0; c < 4; c++) {
+            float v[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; i++) unpack2(acc[i][c], v[i][0], v[i][1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = j0 + (c < 2 ? jc * 4 + 2 * c + h : 32 + jc * 4 + 2 * (c - 2) + h);
+                float *row = xout + j * 32;
+                *reinterpret_cast<float4 *>(row + ((er ^ sw) << 2)) =
+                    make_float4(activate_t<KIND>(v[0][h]), activate_t<KIND>(v[1][h]), activate_t<KIND>(v[2][h]),
+                                activate_t<KIND>(v[3][h]));
+                *reinterpret_cast<float4 *>(row + (((4 + er) ^ sw) << 2)) =
+                    make_float4(activate_t<KIND>(v[4][h]), activate_t<KIND>(v[5][h]), activate_t<KIND>(v[6][h]),
+                                activate_t<KIND>(v[7][h]));
+            }
         }
     }
 }
@@ -283,8 +354,8 @@ __device__ __forceinline__ void mlp_forward_tiled(const MlpDesc &M, const float 
     for (int l = 0; l + 1 < L; l++) {
         const float *Wt = W + M.t_off[l];
         const int K = M.t_rows[l], N = M.t_n[l];
-        const float *xin = (l & 1) ? buf1 : buf0;
-        float *xout = (l & 1) ? buf0 : buf1;
+        const float *xin = (l & 1) && !M.t_inplace ? buf1 : buf0;
+        float *xout = (l & 1) || M.t_inplace ? buf0 : buf1;
         switch (M.activation) {
         case QT_ACT_TANH: tile_layer<QT_ACT_TANH>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
         case QT_ACT_ELU: tile_layer<QT_ACT_ELU>(Wt, Wt + K * N, K, N, xin, xout, er, jc); break;
@@ -294,7 +365,7 @@ __device__ __forceinline__ void mlp_forward_tiled(const MlpDesc &M, const float 
         __syncwarp();
     }
     // output layer: four units, evaluated by each lane for its own episode
-    const float *xin = ((L - 1) & 1) ? buf1 : buf0;
+    const float *xin = ((L - 1) & 1) && !M.t_inplace ? buf1 : buf0;
     const float *Wo = W + M.t_off[L - 1];
     const int rows_o = M.t_rows[L - 1];
     float o[4];
@@ -630,8 +701,13 @@ static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, PolicyArg
     DynConsts C;
     C.init(P);
     too_wide = false;
-    if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024)
+    if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024) {
+        // three resident blocks (168 registers, the env state spills to L1 across the network evaluation)
+        // when the shared memory allows, else two or one
+        if (QT_POLICY_TILED_3 && smem_plan_tiled(M) <= 74 * 1024)
+            return launch_policy_as<MOTION, 3, true>(P, C, M, A, smem_plan_tiled(M), st);
         return launch_policy_as<MOTION, 2, true>(P, C, M, A, smem_plan_tiled(M), st);
+    }
     const size_t smem = smem_plan(M, A.w_in_smem);
     if (smem > 200 * 1024) {
         too_wide = true;
