@@ -148,7 +148,9 @@ __device__ __forceinline__ float activate_t(float x) {
     if (KIND == QT_ACT_TANH) return tanhf(x);
     if (KIND == QT_ACT_ELU) return x > 0.0f ? x : expm1f(x);
     if (KIND == QT_ACT_LEAKY_RELU) return x > 0.0f ? x : 0.1f * x;
-    return x != x ? x : fmaxf(x, 0.0f);   // torch.relu propagates NaN, fmaxf does not
+    float r;   // torch.relu propagates NaN, fmaxf does not; max.NaN does, in one instruction
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // Activate a finished chunk and either store it (hidden layer) or multiply it into the output
@@ -369,9 +371,23 @@ __device__ __forceinline__ void mlp_forward_tiled(const MlpDesc &M, const float 
     const float *Wo = W + M.t_off[L - 1];
     const int rows_o = M.t_rows[L - 1];
     float o[4];
-    chunk_bias<4>(Wo + rows_o * 4, 0, o);
-#pragma unroll 4
-    for (int k = 0; k < rows_o; k++) chunk_fma<4>(Wo + k * 4, xin[tile_elem(k, lane)], o);
+    {
+        const float4 b = *reinterpret_cast<const float4 *>(Wo + rows_o * 4);
+        unsigned long long o01 = pack2(b.x, b.y), o23 = pack2(b.z, b.w);
+        const float *xl = xin + (lane & 3);
+        for (int g = 0; g < (rows_o >> 2); g++) {   // rows_o is a multiple of 64; one swizzle per four rows
+            const float *xr = xl + g * 128 + ((((lane >> 2) ^ g) & 7) << 2);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float4 w = *reinterpret_cast<const float4 *>(Wo + (g * 4 + r) * 4);
+                const float x = xr[r * 32];
+                ffma2(x, pack2(w.x, w.y), o01);
+                ffma2(x, pack2(w.z, w.w), o23);
+            }
+        }
+        unpack2(o01, o[0], o[1]);
+        unpack2(o23, o[2], o[3]);
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float sg = 1.0f / (1.0f + expf(-o[i]));  // torch.sigmoid
