@@ -95,6 +95,21 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
     return true;
 }
 
+// Two fp32 FMAs in one instruction (sm_100 FFMA2): acc.lo += a * w.lo, acc.hi += a * w.hi, each rounded
+// exactly like fmaf.  The FP32 pipe does the same work either way; what halves is the number of issue
+// slots the 5 504 FMAs of a 64-64 network take, and the tiled kernel is issue-bound.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(float a, unsigned long long w, unsigned long long &acc) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(a, a)), "l"(w));   // in place: no accumulator copies
+}
+
 template <int CH>
 __device__ __forceinline__ void chunk_bias(const float *__restrict__ bias, int j0, float (&acc)[CH]) {
 #pragma unroll
@@ -112,10 +127,11 @@ __device__ __forceinline__ void chunk_fma(const float *__restrict__ w, float xk,
 #pragma unroll
     for (int i = 0; i < CH; i += 4) {
         const float4 wk = *reinterpret_cast<const float4 *>(w + i);
-        acc[i] = fmaf(xk, wk.x, acc[i]);
-        acc[i + 1] = fmaf(xk, wk.y, acc[i + 1]);
-        acc[i + 2] = fmaf(xk, wk.z, acc[i + 2]);
-        acc[i + 3] = fmaf(xk, wk.w, acc[i + 3]);
+        unsigned long long lo = pack2(acc[i], acc[i + 1]), hi = pack2(acc[i + 2], acc[i + 3]);
+        ffma2(xk, pack2(wk.x, wk.y), lo);
+        ffma2(xk, pack2(wk.z, wk.w), hi);
+        unpack2(lo, acc[i], acc[i + 1]);
+        unpack2(hi, acc[i + 2], acc[i + 3]);
     }
 }
 
@@ -238,21 +254,6 @@ __device__ __forceinline__ void mlp_forward(const MlpDesc &M, const float *__res
 // epilogue, the float4 loads of the k-loop and the per-episode scalar accesses all conflict free.
 __device__ __forceinline__ int tile_elem(int row, int lane) {   // float index of (unit row, episode lane)
     return row * 32 + ((((lane >> 2) ^ (row >> 2)) & 7) << 2) + (lane & 3);
-}
-
-// Two fp32 FMAs in one instruction (sm_100 FFMA2): acc.lo += a * w.lo, acc.hi += a * w.hi, each rounded
-// exactly like fmaf.  The FP32 pipe does the same work either way; what halves is the number of issue
-// slots the 5 504 FMAs of a 64-64 network take, and the tiled kernel is issue-bound.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ void ffma2(float a, unsigned long long w, unsigned long long &acc) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2(a, a)), "l"(w));   // in place: no accumulator copies
 }
 
 template <int KIND>
