@@ -195,6 +195,10 @@ def _validate_path(path: Path) -> None:
         raise ValueError(f"Path contains null byte: {path}")
 
 
+_Q_POS_DEFAULT, _Q_VEL_DEFAULT = [0.0001, 0.0001, 16.0], [0.0036, 0.0036, 4.0]   # riccati_lqr.py:624-625
+_Q_INT_DEFAULT, _R_DEFAULT = [0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0]
+
+
 class ControllerTuner:
     """tuning.py:581-1442 for the Riccati-LQR / LQI (and heuristic LQR) controllers."""
 
@@ -344,14 +348,13 @@ class ControllerTuner:
             return torch.as_tensor(np.stack(ks), dtype=torch.float64, device=ctx.device), proto
         lqi = bool(configs[0].get("use_lqi", False))
         n = 9 if lqi else 6
+        # one numpy conversion per field (a per-candidate loop costs ~100 ms for a 65 536-candidate sweep)
         q = np.empty((C, n))
-        r = np.empty((C, 4))
-        for i, c in enumerate(configs):
-            q[i, 0:3] = c.get("q_pos", [0.0001, 0.0001, 16.0])
-            q[i, 3:6] = c.get("q_vel", [0.0036, 0.0036, 4.0])
-            if lqi:
-                q[i, 6:9] = c.get("q_int", [0.0, 0.0, 0.0])
-            r[i] = c.get("r_controls", [1.0, 1.0, 1.0, 1.0])
+        q[:, 0:3] = np.asarray([c.get("q_pos", _Q_POS_DEFAULT) for c in configs], dtype=np.float64)
+        q[:, 3:6] = np.asarray([c.get("q_vel", _Q_VEL_DEFAULT) for c in configs], dtype=np.float64)
+        if lqi:
+            q[:, 6:9] = np.asarray([c.get("q_int", _Q_INT_DEFAULT) for c in configs], dtype=np.float64)
+        r = np.asarray([c.get("r_controls", _R_DEFAULT) for c in configs], dtype=np.float64).reshape(C, 4)
         f64 = dict(dtype=torch.float64, device=ctx.device)
         qd, rd = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
         A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
@@ -406,9 +409,9 @@ class ControllerTuner:
         ctx.reduce_scores(metrics, C, eps, cand)
         host = cand.cpu().numpy()
         self.last_metrics = metrics
-        scores = [float(x) for x in host[0]]
-        out = [{"mean_on_target_ratio": float(host[1, i]), "mean_tracking_error": float(host[2, i]),
-                "success_rate": float(host[3, i]), "episodes_evaluated": eps} for i in range(C)]
+        scores = host[0].tolist()
+        out = [{"mean_on_target_ratio": a, "mean_tracking_error": b, "success_rate": c_, "episodes_evaluated": eps}
+               for a, b, c_ in zip(host[1].tolist(), host[2].tolist(), host[3].tolist())]
         return scores, out
 
     # -- search loops ----------------------------------------------------------------------------------

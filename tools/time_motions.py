@@ -5,7 +5,7 @@ ctx = _lib.get_context()
 E = 1 << 20
 seeds = torch.arange(E, dtype=torch.int64, device=ctx.device) + 42
 for cfg in ({}, {"use_lqi": True, "q_int": [0.01, 0.01, 0.1]}):
-    for motion in ("linear", "circular", "sinusoidal", "figure8"):
+    for motion in ("stationary", "linear", "circular", "sinusoidal", "figure8"):
         env = EnvConfig(); env.target.motion_type = motion
         ctrl = RiccatiLQRController(config=cfg)
         for _ in range(2): rollout_device(ctrl, env, SuccessCriteria(), seeds)
