@@ -185,7 +185,7 @@ def run_reference_arm(args) -> None:
         "note": "The reference itself is single-threaded Python (~4.5e3 env-steps/s/core, BASELINE.md); it cannot "
                 "travel to the GPU box, so this arm times its C restatement, a far stronger CPU baseline.",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def ctx_sm_count(ctx) -> int:
@@ -417,12 +417,31 @@ def run_gpu_arm(args) -> None:
         "gpu_launches": int(gpu_launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare, "policy": policy,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main() -> None:
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL prints
+    # "NCCL version ..." there at communicator creation) is sent to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
