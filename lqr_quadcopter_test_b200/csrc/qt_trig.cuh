@@ -60,6 +60,7 @@ QT_TRIG_CONST double c_trig[32] = {
 constexpr double kShiftMax = 0.26;        // full Taylor polynomials: truncation error < 1e-17 up to here
 constexpr double kShiftSmall = 0.0078125;  // 2^-7: sin through d^5, cos through d^6 suffice (< 4e-19)
 constexpr double kShiftTiny = 0.0009765625;  // 2^-10: sin through d^3, cos through d^4 suffice (< 8e-18)
+constexpr double kShiftMid = 0.03125;        // 2^-5: sin through d^7, cos through d^8 suffice (< 8e-20)
 
 // Out-of-line so the (practically never taken) huge-argument path costs the hot loop one
 // predicated call instead of an inlined Payne-Hanek reduction.
@@ -110,7 +111,7 @@ QT_TRIG_FN void sincos_pi(double x, double &s, double &c) {
 // sin/cos of `arg`, given sin/cos of `base`, where arg = fl(base + small increment) and the
 // caller guarantees |arg - base| <= kShiftMax (SMALL = false) or <= kShiftSmall (SMALL = true:
 // two Taylor terms fewer per polynomial, truncation error < 4e-19).
-// TIER 0: |d| <= kShiftMax, 1: |d| <= kShiftSmall, 2: |d| <= kShiftTiny
+// TIER 0: |d| <= kShiftMax, 1: |d| <= kShiftSmall, 2: |d| <= kShiftTiny, 3: |d| <= kShiftMid
 template <int TIER>
 QT_TRIG_FN void sincos_shifted_d(double sb, double cb, double d, double &s, double &c);
 
@@ -134,6 +135,11 @@ QT_TRIG_FN void sincos_shifted_d(double sb, double cb, double d, double &s, doub
     if (TIER == 1) {
         p = fma(z, c_trig[17], c_trig[16]);
         q = fma(z, c_trig[23], c_trig[22]);
+    } else if (TIER == 3) {
+        p = fma(z, c_trig[18], c_trig[17]);
+        q = fma(z, c_trig[24], c_trig[23]);
+        p = fma(z, p, c_trig[16]);
+        q = fma(z, q, c_trig[22]);
     } else {
         p = fma(z, c_trig[20], c_trig[19]);
         q = fma(z, c_trig[26], c_trig[25]);

@@ -9,7 +9,9 @@ extern "C" void trig_shifted_host(const double *base, const double *arg, long n,
     for (long i = 0; i < n; i++) {
         double sb, cb;
         qt::sincos_pi(base[i], sb, cb);
-        if (tier == 2)
+        if (tier == 3)
+            qt::sincos_shifted<3>(base[i], sb, cb, arg[i], s[i], c[i]);
+        else if (tier == 2)
             qt::sincos_shifted<2>(base[i], sb, cb, arg[i], s[i], c[i]);
         else if (tier == 1)
             qt::sincos_shifted<1>(base[i], sb, cb, arg[i], s[i], c[i]);

@@ -47,7 +47,7 @@ def test_special_arguments(shim):
     assert np.isnan(s[7:]).all() and np.isnan(c[7:]).all()
 
 
-@pytest.mark.parametrize("small,bound", [(2, 0.0009765625), (1, 0.0078125), (0, 0.26)])
+@pytest.mark.parametrize("small,bound", [(2, 0.0009765625), (1, 0.0078125), (3, 0.03125), (0, 0.26)])
 def test_shifted_evaluation_matches_direct_evaluation(shim, small, bound):
     """sin/cos(fl(base + delta)) from sin/cos(base): the RK4 stage angles of qt_step.cuh."""
     rng = np.random.default_rng(2)
