@@ -20,8 +20,12 @@ for r in rows:
     if len(r) <= iss or not r[il].isdigit():
         continue            # rows with an empty line number are the SASS instructions of the line above
     key = (fpath, int(r[il]))
-    agg[key][0] += float(r[ie] or 0)
-    agg[key][1] += float(r[iss] or 0)
+    try:   # source lines with quotes and commas (inline asm) can shift the CSV columns: skip those rows
+        e, st = float(r[ie] or 0), float(r[iss] or 0)
+    except ValueError:
+        continue
+    agg[key][0] += e
+    agg[key][1] += st
     agg[key][2] = r[isrc].strip()[:90]
 ti = sum(v[0] for v in agg.values())
 ts = sum(v[1] for v in agg.values())
