@@ -248,3 +248,32 @@ def test_cma_es_specification_and_convergence(tmp_path):
         assert len(X) == es.lam
         es.tell(X, [es.penalised(x, f(es.repair(x))) for x in X])
     assert es.best_f < 1e-9 and np.all(es.best_x >= lo) and np.all(es.best_x <= hi)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line on stdout with the
+    contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import pathlib
+    import subprocess
+    import sys
+
+    ROOT = pathlib.Path(__file__).resolve().parent.parent
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 1e6
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+    env["RANK"] = "1"
+    r1 = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, env=env, timeout=300)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
