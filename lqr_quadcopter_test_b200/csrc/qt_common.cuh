@@ -10,6 +10,8 @@ struct qt_context {
     int device;
     cudaStream_t stream;      // stream work is enqueued on
     cudaStream_t own_stream;  // created by qt_create, destroyed by qt_destroy
+    cudaStream_t aux_stream;  // second lane of the host-buffer entry points' copy/compute pipeline
+    cudaEvent_t ev_inputs, ev_aux_done;  // ordering between the two lanes (timing disabled)
     int sm_count;
     int64_t launches;
     // scratch owned by the library (host-buffer entry points only; never handed to the caller)
