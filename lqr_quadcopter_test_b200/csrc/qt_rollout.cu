@@ -21,6 +21,9 @@
 namespace qt {
 
 constexpr int kRolloutThreads = 128;
+#ifndef QT_OPT_KREG
+#define QT_OPT_KREG 1
+#endif
 #ifndef QT_ROLLOUT_MIN_BLOCKS
 #define QT_ROLLOUT_MIN_BLOCKS 4  // resident blocks per SM the register allocator must allow (128 registers)
 #endif
@@ -156,13 +159,32 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 
         auto step_loop = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
+#if QT_OPT_KREG
+        // the structured LQR law uses six gain entries: keep them in registers (same layout, so ctrl_action's
+        // constant indices resolve to registers) instead of six loads at the top of every step
+        double kreg[4 * KC];
+        const double *Kc = Kp;
+        if constexpr (FAST && (CTRL == CK_LQR || (QT_OPT_KREG > 1 && CTRL == CK_LQI))) {
+#pragma unroll
+            for (int i = 0; i < 4 * KC; i++) kreg[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < KC; c += 3) {
+                kreg[0 * KC + c + 2] = Kp[0 * KC + c + 2];
+                kreg[1 * KC + c + 1] = Kp[1 * KC + c + 1];
+                kreg[2 * KC + c + 0] = Kp[2 * KC + c + 0];
+            }
+            Kc = kreg;
+        }
+#else
+        const double *Kc = Kp;
+#endif
         while (term == QT_TERM_NONE && step < A.max_steps) {
             // ---- controller on the pre-step observation
             double act[4];
             if constexpr (CTRL == CK_PID)
                 pid_action<FULL>(P, Kp, s, tp, tv, ta, t, integ, last_time, act, ffg);
             else
-                ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kp, s, tp, tv, ta, err_pre, integ, saturations, act, ffg);
+                ctrl_action<CTRL == CK_LQI, FULL, FAST>(P, Kc, s, tp, tv, ta, err_pre, integ, saturations, act, ffg);
 
             // ---- metrics sample k = step (pre-step observation, eval.py:142-159); the control effort's
             // square root is taken together with the tracking error's at the end of the step (sqrt_pair)
