@@ -369,7 +369,8 @@ def run_gpu_arm(args) -> None:
 
         torch.manual_seed(0)
         pol = DeepTrackingPolicy(config={"hidden_sizes": [64, 64], "activation": "relu"})
-        Ep = min(E, 1 << 17)
+        # whole waves of the policy kernel's grid: 3 resident blocks of 128 episodes per SM, 4 waves (227 328 on a B200)
+        Ep = min(E, ctx_sm_count(ctx) * 3 * 128 * 4)
         pseeds = torch.arange(Ep, dtype=torch.int64, device=dev) + 42
         for _ in range(2):
             rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
