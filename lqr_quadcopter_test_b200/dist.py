@@ -111,6 +111,31 @@ def gather_candidate_scores(local_cand, total_candidates: int):
     return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, widths)], dim=1)
 
 
+def evaluate_candidates_sharded(tuner, configs: list[dict]) -> tuple[list[float], list[dict]]:
+    """ControllerTuner.evaluate_configs over all ranks (BASELINE config 4: the candidates of a Q/R sweep,
+    each with its DARE solve and its evaluation episodes, split contiguously over the GPUs).  Rank r scores
+    candidates [lo, hi) — every candidate sees the same episode seeds wherever it runs (tuning.py:875), so
+    the scores do not depend on the partition — and one all_gather of the [4, C_local] score rows gives
+    every rank the full lists, in candidate order."""
+    import torch
+    import torch.distributed as dist
+
+    rank, size, _ = world()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tuner.evaluate_configs(configs)
+    C = len(configs)
+    lo, hi = shard_range(C, rank, size)
+    scores, metrics = tuner.evaluate_configs(configs[lo:hi]) if hi > lo else ([], [])
+    eps = metrics[0]["episodes_evaluated"] if metrics else int(tuner.config.evaluation_episodes)
+    rows = np.array([scores, [m["mean_on_target_ratio"] for m in metrics], [m["mean_tracking_error"] for m in metrics],
+                     [m["success_rate"] for m in metrics]], dtype=np.float64).reshape(4, hi - lo)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    full = gather_candidate_scores(torch.as_tensor(rows, device=dev), C).cpu().numpy()
+    out = [{"mean_on_target_ratio": a, "mean_tracking_error": b, "success_rate": c, "episodes_evaluated": eps}
+           for a, b, c in zip(full[1].tolist(), full[2].tolist(), full[3].tolist())]
+    return full[0].tolist(), out
+
+
 def argmax_first(scores: np.ndarray) -> int:
     """Best candidate with the reference's tie rule (strict '>' while scanning, tuning.py:1084)."""
     return int(np.argmax(scores))

@@ -436,7 +436,11 @@ class ControllerTuner:
         else:
             remaining = cfg.max_iterations - len(self.results)
             configs = [self._generate_random_config() for _ in range(max(remaining, 0))]
-        scores, metrics = self.evaluate_configs(configs)
+        # under torchrun the candidates are split over the ranks (one all_gather of the score rows at the end);
+        # every rank draws the same candidate list from the same seed and ends with the same result
+        from .dist import evaluate_candidates_sharded
+
+        scores, metrics = evaluate_candidates_sharded(self, configs)
         for c, s, m in zip(configs, scores, metrics):
             self._record_result(c, s, m)
         result = TuningResult(

@@ -33,6 +33,27 @@ def _worker(rank, size, port, total, out_q):
     clo, chi = qd.shard_range(C, rank, size)
     cand = torch.arange(4 * C, dtype=torch.float64).reshape(4, C)[:, clo:chi].contiguous()
     full = qd.gather_candidate_scores(cand, C)
+
+    # the tuner's sharded candidate evaluation with a stand-in for the GPU evaluation: candidate order, metrics
+    # dictionaries and unequal shards
+    class FakeTuner:
+        class config:
+            evaluation_episodes = 3
+
+        calls = []
+
+        def evaluate_configs(self, cfgs):
+            self.calls.append(len(cfgs))
+            return ([c["x"] * 0.5 for c in cfgs],
+                    [{"mean_on_target_ratio": c["x"] / 100, "mean_tracking_error": 1.0 + c["x"], "success_rate": 1.0,
+                      "episodes_evaluated": 3} for c in cfgs])
+
+    ft = FakeTuner()
+    cfgs = [{"x": float(i)} for i in range(7)]
+    sc, me = qd.evaluate_candidates_sharded(ft, cfgs)
+    assert ft.calls == [4 if rank == 0 else 3]
+    assert sc == [0.5 * i for i in range(7)] and [m["mean_tracking_error"] for m in me] == [1.0 + i for i in range(7)]
+    assert all(m["episodes_evaluated"] == 3 and m["success_rate"] == 1.0 for m in me)
     out_q.put((rank, summary.mean_on_target_ratio, summary.std_on_target_ratio, summary.best_episode_idx,
                summary.worst_episode_idx, summary.total_episodes, full.numpy().tolist()))
     torch.distributed.destroy_process_group()
