@@ -92,6 +92,20 @@ def evaluate_sharded(evaluator, num_episodes: int, base_seed: int = 42, max_step
     return summary, out["metrics"]
 
 
+def teacher_dataset_sharded(controller, env_config=None, num_episodes: int = 1 << 22, base_seed: int = 42,
+                            stride: int = 10, **kw):
+    """BASELINE config 5 over all ranks: rank r emits the teacher data set of episodes [lo, hi) (seeds
+    base_seed + index) into its own GPU's tensors — 4 M episodes at stride 10 are 111 GB in all, 13.8 GB per GPU
+    on eight — and no collective is needed: each rank hands its shard to its own trainer process.
+    Returns ``(features, actions, metrics, (lo, hi))``."""
+    from .dataset import teacher_dataset
+
+    rank, size, _ = world()
+    lo, hi = shard_range(num_episodes, rank, size)
+    f, a, m = teacher_dataset(controller, env_config, num_episodes=hi - lo, base_seed=int(base_seed) + lo, stride=stride, **kw)
+    return f, a, m, (lo, hi)
+
+
 def gather_candidate_scores(local_cand, total_candidates: int):
     """Tuning: each rank scored candidates [lo, hi); gather the [4, C_local] rows into [4, C] on every
     rank (an all_gather of <= 2 MiB for 65 536 candidates).  Shards may differ by one candidate, so
