@@ -263,3 +263,26 @@ def test_hyperparameter_sweep_ranks_configurations(gpu_ctx, tmp_path):
     assert ranked[0]["mean_on_target_ratio"] > ranked[1]["mean_on_target_ratio"]
     saved = json.loads((tmp_path / "out" / "sweep_results.json").read_text())
     assert [r["name"] for r in saved] == ["riccati", "pid"]
+
+
+def test_teacher_dataset_shards_are_slices_of_the_whole(gpu_ctx, monkeypatch):
+    """dist.teacher_dataset_sharded (BASELINE config 5 per rank): the shard of rank r is exactly the rows of
+    episodes [lo, hi) of the single-process data set; no collective is involved, the torchrun environment
+    variables alone select the slice."""
+    import torch
+
+    from lqr_quadcopter_test_b200 import EnvConfig, RiccatiLQRController, teacher_dataset
+    from lqr_quadcopter_test_b200 import dist as qd
+
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    ctrl = RiccatiLQRController(config={})
+    E = 1001
+    f, a, m = teacher_dataset(ctrl, env, num_episodes=E, base_seed=7, stride=25, max_steps=500, flatten=False)
+    for rank in range(3):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("WORLD_SIZE", "3")
+        fs, as_, ms, (lo, hi) = qd.teacher_dataset_sharded(ctrl, env, num_episodes=E, base_seed=7, stride=25,
+                                                          max_steps=500, flatten=False)
+        assert (lo, hi) == qd.shard_range(E, rank, 3)
+        assert torch.equal(fs, f[:, lo:hi]) and torch.equal(as_, a[:, lo:hi]) and torch.equal(ms, m[:, lo:hi])
