@@ -50,11 +50,16 @@ enum ColdRow { CR_SUM_ERR = 0, CR_SUM_ERR2, CR_SUM_EFF, CR_OV_CUR, CR_OV_MAX, CR
 constexpr int CR_TARGET_TRIG = CR_TARGET + QT_TARGET_PARAMS;  // 6 rows: carried sin/cos of the pattern angles
 constexpr int kColdRows = CR_TARGET_TRIG + 6;
 
-template <int MOTION, int CTRL, bool FULL>
+// MODE 0 (lean): metrics only.  MODE 1 (full): feedforward, Euler integrator, trajectory log, data set.
+// MODE 2 (data): the lean loop plus the teacher data set rows (BASELINE config 5) — the full variant's extra
+// live state (target acceleration, feedforward gains, integrator switch, trajectory cursor) costs the
+// register-bound loop far more than the rows themselves.
+template <int MOTION, int CTRL, int MODE>
 __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     rollout_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                    const __grid_constant__ RolloutArgs A) {
     extern __shared__ double smem[];
+    constexpr bool FULL = MODE == 1, DATA = MODE != 0;
     constexpr int KC = CtrlCols<CTRL>::value;
     constexpr int T = kRolloutThreads;
     const int64_t E = A.E;
@@ -232,6 +237,8 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 #pragma unroll
                     for (int i = 0; i < 4; i++) row[(int64_t)(QT_TRAJ_ACTION + i) * E] = act[i];
                 }
+            }
+            if constexpr (DATA) {
                 if (A.feat && step == next_data && data_slot < A.data_slots) {
                     // deep_tracking_policy.py:241-286 feature layout, fp32
                     float2 *f = reinterpret_cast<float2 *>(A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM);
@@ -344,26 +351,30 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     }
 }
 
-template <int MOTION, int CTRL, bool FULL>
+template <int MOTION, int CTRL, int MODE>
 static cudaError_t launch_one(const qt_params &P, const RolloutArgs &A, size_t smem, cudaStream_t st) {
     const int64_t blocks = (A.n_chains + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks <= 0) return cudaSuccess;
     DynConsts C;
     C.init(P);
-    rollout_kernel<MOTION, CTRL, FULL><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, C, A);
+    rollout_kernel<MOTION, CTRL, MODE><<<(unsigned)blocks, kRolloutThreads, smem, st>>>(P, C, A);
     return cudaGetLastError();
 }
 
+template <int MOTION, int CTRL>
+static cudaError_t launch_mode(const qt_params &P, const RolloutArgs &A, size_t smem, int mode, cudaStream_t st) {
+    if (mode == 1) return launch_one<MOTION, CTRL, 1>(P, A, smem, st);
+    if (mode == 2) return launch_one<MOTION, CTRL, 2>(P, A, smem, st);
+    return launch_one<MOTION, CTRL, 0>(P, A, smem, st);
+}
+
 template <int MOTION>
-static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_t smem, bool full,
+static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_t smem, int mode,
                                  cudaStream_t st) {
     switch (ctrl_kind_of(P)) {
-    case CK_PID:
-        return full ? launch_one<MOTION, CK_PID, true>(P, A, smem, st) : launch_one<MOTION, CK_PID, false>(P, A, smem, st);
-    case CK_LQI:
-        return full ? launch_one<MOTION, CK_LQI, true>(P, A, smem, st) : launch_one<MOTION, CK_LQI, false>(P, A, smem, st);
-    default:
-        return full ? launch_one<MOTION, CK_LQR, true>(P, A, smem, st) : launch_one<MOTION, CK_LQR, false>(P, A, smem, st);
+    case CK_PID: return launch_mode<MOTION, CK_PID>(P, A, smem, mode, st);
+    case CK_LQI: return launch_mode<MOTION, CK_LQI>(P, A, smem, mode, st);
+    default: return launch_mode<MOTION, CK_LQR>(P, A, smem, mode, st);
     }
 }
 
@@ -430,8 +441,8 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     }
     // the per-thread cold-state tile (kColdRows x 128 doubles = 17 KB) + staged gains
     const size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
-    const bool full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 ||
-                      traj_out_dev != nullptr || feat_out_dev != nullptr;
+    const bool needs_full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 || traj_out_dev != nullptr;
+    const int full = needs_full ? 1 : (feat_out_dev != nullptr ? 2 : 0);   // kernel MODE
 
     DeviceGuard guard(ctx->device);
     cudaError_t err;
