@@ -375,13 +375,13 @@ def run_gpu_arm(args) -> None:
         for _ in range(2):
             rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
         torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(3):
+        pev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        pev[0].record()
+        for i in range(5):
             pout = rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
-        p1.record()
+            pev[i + 1].record()
         torch.cuda.synchronize()
-        p_ms = p0.elapsed_time(p1) / 3
+        p_ms = statistics.median(pev[i].elapsed_time(pev[i + 1]) for i in range(5))   # secondary figure: median of five
         p_steps = float(pout["metrics"][0].sum().item())
         fma_per_step = 18 * 64 + 64 * 64 + 64 * 4
         fp32_peak = ctx_sm_count(ctx) * 128 * 2 * (clock_info.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
