@@ -4,15 +4,23 @@
 //     features = controller._extract_features(obs); action = network(features); env.step(action)
 // (controllers/deep_tracking_policy.py:199-286, eval.py:119-165, train.py:668-721) by one kernel
 // launch for all episodes: one thread per episode, the env in fp64 exactly as in qt_rollout.cu (same
-// device functions), the network in fp32 like torch.  The packed weights are staged in shared memory
-// (they are read by every thread at the same address: broadcast loads).  The 18 features stay in
-// registers for the first layer; hidden activations live in the thread's own column of a
-// shared-memory tile (two tiles, alternating, only when there are three or more hidden layers); every
-// chunk of 16 output units accumulates in registers, so one weight vector load feeds four FFMAs; and
-// the last hidden layer is never stored — each chunk of it is multiplied into the four output
-// accumulators as soon as it is activated.  For the default 64-64 network that leaves one 32 KB tile
-// + 22 KB of weights per block, i.e. four resident blocks per SM.  This is batch-of-vectors work with
-// fp32-accuracy requirements (the parity target is torch's fp32 Linear); it stays on the FP32 pipe.
+// device functions), the network in fp32 like torch (the parity target is torch's fp32 Linear, so it
+// stays on the FP32 pipe: TF32 / BF16 tensor-core products would miss that target by 1e-3).
+//
+// Two evaluations of the network, identical bit for bit (same products added in the same order):
+//  * TILED — the reference's default 64-64 network and every shape whose hidden widths are within 25 %
+//    of multiples of 64.  The 32 episodes of a warp x the units of a layer form a small GEMM; every
+//    lane owns an 8-episode x 8-unit register tile, one k-step is four 16-byte shared-memory loads for
+//    32 packed FFMA2 (= 64 FMAs); activations travel between layers through per-warp shared-memory
+//    buffers with an XOR swizzle that keeps every access pattern conflict free (tile_layer,
+//    mlp_forward_tiled below).  64-64: 22 KB of staged weights + 8 KB of activations per warp, three
+//    resident blocks per SM.
+//  * PER-THREAD — any other shape and qt_policy_action_batched.  The packed weights are staged in
+//    shared memory and read by every thread at the same address (broadcast loads); the 18 features
+//    stay in registers for the first layer; hidden activations live in the thread's own column of a
+//    shared-memory tile; every chunk of 16 output units accumulates in registers (one weight vector
+//    load per two FFMA2); the last hidden layer is never stored — each chunk of it is multiplied
+//    into the four output accumulators as soon as it is activated.
 #include "qt_common.cuh"
 #include "qt_step.cuh"
 
