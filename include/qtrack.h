@@ -280,8 +280,11 @@ int qt_reduce_summary(qt_context *ctx, const double *metrics_dev, int64_t E, dou
 
 /* ---- host-buffer convenience: Evaluator.evaluate(num_episodes, base_seed) -------------------
  * eval.py:169-231 with HOST buffers: seeds_host [E] in, K_host [4][k_cols] in,
- * metrics_host [16][E] out.  Does H2D, reset, rollout, D2H on the context's stream and
- * returns when metrics_host is valid.                                                        */
+ * metrics_host [16][E] out.  Does H2D, reset, rollout, D2H and returns when metrics_host is valid.
+ * Large batches (E >= 2^17, chain = 1) run as four chunks that alternate between the context's
+ * stream and a second stream owned by the context, so that a chunk's read-back overlaps the next
+ * chunks' kernels; results do not depend on the chunking.  Pinned host buffers make the copies
+ * asynchronous; pageable ones work but serialise.                                               */
 int qt_evaluate_host(qt_context *ctx, const qt_params *params, const uint64_t *seeds_host,
                      int64_t E, int64_t max_steps, int64_t chain, const double *K_host,
                      int32_t k_cols, double *metrics_host);
