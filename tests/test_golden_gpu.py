@@ -54,7 +54,6 @@ def test_rollouts_match_reference(golden, gb):
     """A2-A10 fused: metrics, final state and sampled trajectory of every fixture case."""
     g = golden["rollouts"]
     names = gc.case_names(g)
-    borderline = 0
     for name in names:
         prm, max_steps, chain, tol, _cfg, _env, _crit = gc.case(name)
         cs = np.zeros((4, 1)) if chain > 1 else None
@@ -72,7 +71,6 @@ def test_rollouts_match_reference(golden, gb):
             gb.rollout(prm, g[name + "_state0"], g[name + "_tparams"], g[name + "_K"], max_steps=max_steps,
                        ctrl_state=cs1)
             np.testing.assert_allclose(cs1[0:3], g[name + "_integral"], rtol=0, atol=tol, err_msg=name)
-    assert borderline == 0
 
 
 def test_step_edge_cases_match_reference(golden, gb):

@@ -252,7 +252,6 @@ def test_full_size_properties_one_million_linear_episodes(golden, gb):
     # scalar multiplies by the reciprocal and turns 2400/3000 into 0.7999999999999999)
     Mh = M.cpu().numpy()
     np.testing.assert_array_equal((Mh[P.M_MET_ON_TARGET] / 3000.0 >= 0.8).astype(float), Mh[P.M_MET_SUCCESS])
-    assert ((Mh[P.M_MET_ON_TARGET] == 2400).sum() > 0) or True
     # determinism, and independence from batch composition: the first 4096 episodes alone give the same bits
     again = rollout_device(ctrl, env, SuccessCriteria(), seeds, want_final_state=True)
     assert torch.equal(again["metrics"], M) and torch.equal(again["final_state"], out["final_state"])

@@ -27,6 +27,10 @@ KEYS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_elapsed.avg",
     "launch__shared_mem_per_block_dynamic",
+    # global-store efficiency (logging kernels): requests, sectors, useful bytes per sector, L2 write hits
+    "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio", "lts__t_sectors_srcunit_tex_op_write.sum",
+    "lts__t_sector_op_write_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_write.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
