@@ -18,6 +18,9 @@
  *   - Work is enqueued on the context's stream (qt_set_stream / qt_get_stream); the *_dev
  *     entry points do not synchronise, the *_host entry points return after their result
  *     has landed in host memory.
+ *   - Threads: a context is one GPU + one stream + library scratch.  The *_host entry points of one
+ *     context serialise on an internal mutex (they pipeline over the context's two streams and share
+ *     its scratch); the *_dev entry points are not locked — use one context per host thread.
  *   - There is no CPU fallback: without a CUDA device qt_create fails.
  */
 #ifndef QTRACK_H
@@ -29,7 +32,7 @@
 extern "C" {
 #endif
 
-#define QT_ABI_VERSION 4
+#define QT_ABI_VERSION 5
 
 #define QT_STATE_DIM 12     /* env/quadcopter_env.py:63-70  [p(3) v(3) roll,pitch,yaw  p,q,r] */
 #define QT_ACTION_DIM 4     /* thrust, roll_rate, pitch_rate, yaw_rate (controllers/base.py:28) */
@@ -181,6 +184,10 @@ int qt_reset_batched(qt_context *ctx, const qt_params *params, const uint64_t *s
                      int64_t E, uint64_t *draws_io_dev, double *state_out_dev,
                      double *tparams_out_dev);
 
+/* seeds_out[i] = seed0 + i, the seed sequence of Evaluator.evaluate (eval.py:200: base_seed + i) and of the tuner
+ * (controllers/tuning.py:875: config.seed + ep), written on the device.                       */
+int qt_fill_seeds(qt_context *ctx, uint64_t *seeds_out_dev, int64_t E, uint64_t seed0);
+
 /* Raw generator access for tests: for each seed, n_uniform doubles from Generator.random()
  * followed (same stream) by n_normal draws of standard_normal().  out [n_uniform+n_normal][E]. */
 int qt_rng_probe(qt_context *ctx, const uint64_t *seeds_dev, int64_t E, int32_t n_uniform,
@@ -246,6 +253,21 @@ int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_
                int64_t traj_slots, float *feat_out_dev, float *act_out_dev,
                int64_t data_stride, int64_t data_slots, const double *ff_gains_dev);
 
+/* ---- A14 fused: one ControllerTuner candidate batch (controllers/tuning.py:846-928) ----------
+ * C candidates x eps episodes in one launch.  Episode (c, ep) — global index c * eps + ep — starts from initial
+ * condition ep: state0 [12][eps], tparams [12][eps] are shared by all candidates, because every candidate sees the
+ * same seeds config.seed + ep (tuning.py:875); the controller is reset before every episode (tuning.py:879).
+ * K [C][4][k_cols], ff_gains [C][6] or NULL (as qt_rollout).
+ *   cand_out [4][C] or NULL: score, mean_on_target_ratio, mean_tracking_error, success_rate — exactly what
+ *     qt_reduce_scores computes from the metric rows (numpy's summation order, tuning.py:912-926).  When eps divides
+ *     128 the reduction runs in the rollout kernel's epilogue (a 128-episode block holds whole candidates) and the
+ *     16 metric rows per episode are never written; otherwise the rows go through qt_reduce_scores.
+ *   metrics_out [16][C*eps] or NULL: the per-episode rows, if the caller wants them as well.     */
+int qt_rollout_sweep(qt_context *ctx, const qt_params *params, int64_t C, int64_t eps, int64_t max_steps,
+                     const double *state0_dev, const double *tparams_dev, const double *K_dev,
+                     int32_t k_cols, double *cand_out_dev, double *metrics_out_dev,
+                     const double *ff_gains_dev);
+
 /* ---- A11: solve_dare -----------------------------------------------------------------------
  * riccati_lqr.py:119-184 for `batch` systems: P solves A'PA - P - A'PB(R+B'PB)^-1 B'PA + Q = 0,
  * K = (R+B'PB)^-1 B'PA.  Row-major fp64; A [n][n], B [n][m], Q [n][n], R [m][m] per system with
@@ -288,6 +310,27 @@ int qt_reduce_summary(qt_context *ctx, const double *metrics_dev, int64_t E, dou
 int qt_evaluate_host(qt_context *ctx, const qt_params *params, const uint64_t *seeds_host,
                      int64_t E, int64_t max_steps, int64_t chain, const double *K_host,
                      int32_t k_cols, double *metrics_host);
+
+/* ---- host-buffer convenience: solve_dare for a batch of HOST matrices (riccati_lqr.py:119-184) --
+ * Same arguments as qt_dare_batched with host pointers; strides must be 0 (one matrix shared by all systems) or
+ * dense (n*n, n*m, m*m).  P_out_host, K_out_host and iters_out_host may be NULL.  Does H2D, validation, solve,
+ * gain, D2H in four chunks alternating between the context's two streams and returns when the outputs are valid. */
+int qt_dare_host(qt_context *ctx, int32_t n, int32_t m, int64_t batch, const double *A_host,
+                 int64_t strideA, const double *B_host, int64_t strideB, const double *Q_host,
+                 int64_t strideQ, const double *R_host, int64_t strideR, double *P_out_host,
+                 double *K_out_host, int32_t *iters_out_host, int32_t *info_out_host);
+
+/* ---- host-buffer convenience: a whole Q/R sweep (controllers/tuning.py:846-928 for C candidates) --
+ * q_host [C][n] = per-candidate diagonal of Q (n = 6: q_pos, q_vel; n = 9 with params->use_lqi: + q_int),
+ * r_host [C][4] = r_controls.  Builds the reference's design matrices with params->ctrl_dt, ctrl_mass and
+ * ctrl_gravity (riccati_lqr.py:187-316), solves the C DAREs, resets eps episodes with seeds seed0 + ep, rolls
+ * out C x eps episodes of at most max_steps steps and reduces them.  cand_out_host [4][C] (as qt_reduce_scores),
+ * K_out_host [C][4][n] or NULL, info_out_host [C] = the DARE info codes: a candidate with info != 0 has no valid
+ * row in cand_out — the caller applies the reference's fallback rule to it (riccati_lqr.py:737-777).   */
+int qt_sweep_host(qt_context *ctx, const qt_params *params, int32_t n, int64_t C, int64_t eps,
+                  uint64_t seed0, int64_t max_steps, const double *q_host, const double *r_host,
+                  double ctrl_mass, double ctrl_gravity, double *cand_out_host, double *K_out_host,
+                  int32_t *info_out_host);
 
 /* ---- the deep tracking policy in the loop ------------------------------------
  * controllers/deep_tracking_policy.py:24-147 (PolicyNetwork): 18 features -> hidden layers with one

@@ -24,6 +24,7 @@ ABI_SYMBOLS = (
     "qt_step_batched", "qt_rollout", "qt_dare_batched", "qt_build_lqr_systems",
     "qt_reduce_scores", "qt_reduce_summary", "qt_evaluate_host", "qt_fp64_peak_probe",
     "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy", "qt_sqrt_pair_probe",
+    "qt_fill_seeds", "qt_rollout_sweep", "qt_dare_host", "qt_sweep_host",
 )
 
 _lib = None
@@ -73,6 +74,10 @@ def load_library() -> C.CDLL:
             "qt_reduce_scores": (C.c_int, [vp, vp, i64, i64, vp]),
             "qt_reduce_summary": (C.c_int, [vp, vp, i64, vp]),
             "qt_evaluate_host": (C.c_int, [vp, PP, vp, i64, i64, i64, vp, i32, vp]),
+            "qt_fill_seeds": (C.c_int, [vp, vp, i64, C.c_uint64]),
+            "qt_rollout_sweep": (C.c_int, [vp, PP, i64, i64, i64, vp, vp, vp, i32, vp, vp, vp]),
+            "qt_dare_host": (C.c_int, [vp, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp]),
+            "qt_sweep_host": (C.c_int, [vp, PP, i32, i64, i64, C.c_uint64, i64, vp, vp, dbl, dbl, vp, vp, vp]),
             "qt_fp64_peak_probe": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]),
             "qt_sqrt_pair_probe": (C.c_int, [vp, i64, vp, vp, vp, vp]),
             "qt_mlp_packed_floats": (i64, [C.POINTER(QtMlp)]),
@@ -189,6 +194,27 @@ class Context:
             _ptr(K), k_cols, k_stride, _ptr(metrics_out), _ptr(ctrl_state_io),
             _ptr(final_state_out), _ptr(traj_out),
             traj_stride, traj_slots, _ptr(feat_out), _ptr(act_out), data_stride, data_slots, _ptr(ff_gains)))
+
+    def fill_seeds(self, seeds_out, seed0):
+        self.check(self.lib.qt_fill_seeds(self.handle, _ptr(seeds_out), seeds_out.numel(), int(seed0) & (2 ** 64 - 1)))
+
+    def rollout_sweep(self, params, C_, eps, max_steps, state0, tparams, K, k_cols, cand_out, metrics_out=None,
+                      ff_gains=None):
+        """C_ candidates x eps episodes sharing the eps initial conditions; cand_out [4, C_] (see include/qtrack.h)."""
+        self.check(self.lib.qt_rollout_sweep(self.handle, C.byref(params), C_, eps, max_steps, _ptr(state0),
+                                             _ptr(tparams), _ptr(K), k_cols, _ptr(cand_out), _ptr(metrics_out),
+                                             _ptr(ff_gains)))
+
+    def dare_host(self, n, m, batch, A, strideA, B, strideB, Q, strideQ, R, strideR, P_out, K_out, iters_out, info_out):
+        """Host (ideally pinned) tensors in and out; returns after the outputs are valid."""
+        self.check(self.lib.qt_dare_host(self.handle, n, m, batch, _ptr(A), strideA, _ptr(B), strideB, _ptr(Q), strideQ,
+                                         _ptr(R), strideR, _ptr(P_out), _ptr(K_out), _ptr(iters_out), _ptr(info_out)))
+
+    def sweep_host(self, params, n, C_, eps, seed0, max_steps, q_host, r_host, ctrl_mass, ctrl_gravity, cand_out_host,
+                   K_out_host, info_out_host):
+        self.check(self.lib.qt_sweep_host(self.handle, C.byref(params), n, C_, eps, int(seed0) & (2 ** 64 - 1), max_steps,
+                                          _ptr(q_host), _ptr(r_host), float(ctrl_mass), float(ctrl_gravity),
+                                          _ptr(cand_out_host), _ptr(K_out_host), _ptr(info_out_host)))
 
     def dare_batched(self, n, m, batch, A, strideA, B, strideB, Q, strideQ, R, strideR, P_out,
                      K_out, iters_out, info_out):

@@ -62,9 +62,8 @@ extern "C" int qt_create(int device, qt_context **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return QT_ERR_NO_DEVICE;
     if (device < 0 || device >= count) return QT_ERR_ARG;
-    qt_context *ctx = new (std::nothrow) qt_context();
+    qt_context *ctx = new (std::nothrow) qt_context();   // value-initialised: every plain member is zero
     if (!ctx) return QT_ERR_ARG;
-    memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     DeviceGuard guard(device);
     cudaDeviceProp prop;
@@ -107,6 +106,7 @@ extern "C" void qt_destroy(qt_context *ctx) {
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
+        if (ctx->sweep_scratch_dev) cudaFree(ctx->sweep_scratch_dev);
         if (ctx->partials_dev) cudaFree(ctx->partials_dev);
         if (ctx->aux_stream) {
             cudaStreamSynchronize(ctx->aux_stream);
@@ -148,19 +148,14 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     QT_REQUIRE(ctx, E >= 0, "E < 0");
     QT_REQUIRE(ctx, k_cols == (params->controller_type == QT_CTRL_PID ? 3 : (params->use_lqi ? 9 : 6)), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
     if (E == 0) return QT_OK;
+    std::lock_guard<std::mutex> lock(ctx->host_call_mutex);
     DeviceGuard guard(ctx->device);
     // scratch layout: K (512 bytes reserved) | seeds | state0 [12][E] | tparams [12][E] | metrics [16][E]; every
     // region starts on a 16-byte boundary whatever the parity of E (the rollout reads K as 16-byte pairs)
     const size_t n = (size_t)E, n2 = (n + 1) & ~(size_t)1;
     const size_t off_K = 0, off_seeds = 512, off_state = off_seeds + n2 * 8, off_tp = off_state + 12 * n2 * 8,
                  off_met = off_tp + 12 * n2 * 8, total = off_met + 16 * n2 * 8;
-    if (ctx->scratch_bytes < total) {
-        if (ctx->scratch_dev) QT_CUDA_TRY(ctx, cudaFree(ctx->scratch_dev));
-        ctx->scratch_dev = nullptr;
-        ctx->scratch_bytes = 0;
-        QT_CUDA_TRY(ctx, cudaMalloc(&ctx->scratch_dev, total));
-        ctx->scratch_bytes = total;
-    }
+    if (int rc0 = ensure_scratch(ctx, total)) return rc0;
     char *base = reinterpret_cast<char *>(ctx->scratch_dev);
     uint64_t *seeds_dev = reinterpret_cast<uint64_t *>(base + off_seeds);
     double *state_dev = reinterpret_cast<double *>(base + off_state);
@@ -179,7 +174,7 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     int64_t cuts[5] = {0, E, E, E, E};
     int n_chunks = 1;
     if (chain <= 1 && E >= (1 << 17)) {
-        const int64_t unit = 128 * 148;   // whole waves of blocks per chunk boundary are not needed, whole blocks are
+        const int64_t unit = 128 * (int64_t)ctx->sm_count;   // chunk boundaries on whole blocks (one block per SM each)
         cuts[1] = (E / 2) / unit * unit;
         cuts[2] = cuts[1] + (E / 4) / unit * unit;
         cuts[3] = cuts[2] + (E / 8) / unit * unit;
@@ -217,6 +212,132 @@ extern "C" int qt_evaluate_host(qt_context *ctx, const qt_params *params, const 
     cudaError_t es = cudaStreamSynchronize(user_stream);
     if (rc != QT_OK) return rc;
     if (es != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "cudaStreamSynchronize", cudaGetErrorString(es));
+    return QT_OK;
+}
+
+// solve_dare (riccati_lqr.py:119-184) for HOST matrices: H2D, validation + solve + gain, D2H.  The batch is cut into
+// four chunks that alternate between the context's two streams so the copies of one chunk overlap the solves of
+// its neighbours (inputs are 416 B and outputs 200 B per n = 6 system: at 65 536 systems the PCIe time is of the
+// same order as the 0.5 ms of arithmetic).
+extern "C" int qt_dare_host(qt_context *ctx, int32_t n, int32_t m, int64_t batch, const double *A_host,
+                            int64_t strideA, const double *B_host, int64_t strideB, const double *Q_host,
+                            int64_t strideQ, const double *R_host, int64_t strideR, double *P_out_host,
+                            double *K_out_host, int32_t *iters_out_host, int32_t *info_out_host) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, n >= 1 && n <= QT_MAX_N && m >= 1 && m <= QT_MAX_M, "n must be 1..16, m 1..8");
+    QT_REQUIRE(ctx, batch >= 0 && A_host && B_host && Q_host && R_host && info_out_host, "bad argument");
+    QT_REQUIRE(ctx, (strideA == 0 || strideA == n * n) && (strideB == 0 || strideB == n * m) &&
+                        (strideQ == 0 || strideQ == n * n) && (strideR == 0 || strideR == m * m),
+               "host strides must be 0 (shared) or dense");
+    if (batch == 0) return QT_OK;
+    std::lock_guard<std::mutex> lock(ctx->host_call_mutex);
+    DeviceGuard guard(ctx->device);
+    const size_t nb = (size_t)batch, nn = (size_t)n * n, nm = (size_t)n * m, mm = (size_t)m * m;
+    auto count = [&](int64_t stride, size_t each) { return (stride == 0 ? 1 : nb) * each; };
+    size_t off = 0;
+    auto take = [&](size_t doubles) { size_t o = off; off += ((doubles + 1) & ~(size_t)1) * 8; return o; };
+    const size_t oA = take(count(strideA, nn)), oB = take(count(strideB, nm)), oQ = take(count(strideQ, nn)),
+                 oR = take(count(strideR, mm)), oP = take(P_out_host ? nb * nn : 0), oK = take(nb * nm),
+                 oI = take(nb), oF = take(nb);   // iters / info: int32, half of the reserved doubles
+    if (int rc0 = ensure_scratch(ctx, off)) return rc0;
+    char *base = reinterpret_cast<char *>(ctx->scratch_dev);
+    double *dA = (double *)(base + oA), *dB = (double *)(base + oB), *dQ = (double *)(base + oQ), *dR = (double *)(base + oR);
+    double *dP = P_out_host ? (double *)(base + oP) : nullptr, *dK = (double *)(base + oK);
+    int32_t *dI = (int32_t *)(base + oI), *dF = (int32_t *)(base + oF);
+    cudaStream_t user_stream = ctx->stream;
+    cudaStream_t lanes[2] = {user_stream, ctx->aux_stream};
+    const int n_chunks = batch >= 4096 ? 4 : 1;
+    // shared (stride 0) matrices first, on the user's stream; the second lane waits for them
+    if (strideA == 0) QT_CUDA_TRY(ctx, cudaMemcpyAsync(dA, A_host, nn * 8, cudaMemcpyHostToDevice, user_stream));
+    if (strideB == 0) QT_CUDA_TRY(ctx, cudaMemcpyAsync(dB, B_host, nm * 8, cudaMemcpyHostToDevice, user_stream));
+    if (strideQ == 0) QT_CUDA_TRY(ctx, cudaMemcpyAsync(dQ, Q_host, nn * 8, cudaMemcpyHostToDevice, user_stream));
+    if (strideR == 0) QT_CUDA_TRY(ctx, cudaMemcpyAsync(dR, R_host, mm * 8, cudaMemcpyHostToDevice, user_stream));
+    if (n_chunks > 1) {
+        QT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, user_stream));
+        QT_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_inputs, 0));
+    }
+    int rc = QT_OK;
+    for (int c = 0; c < n_chunks && rc == QT_OK; c++) {
+        const int64_t lo = batch * c / n_chunks, hi = batch * (c + 1) / n_chunks, nc = hi - lo;
+        if (nc <= 0) continue;
+        cudaStream_t st = lanes[c & 1];
+        ctx->stream = st;
+        cudaError_t e = cudaSuccess;
+        auto h2d = [&](double *d, const double *h, int64_t stride, size_t each) {
+            if (stride != 0 && e == cudaSuccess)
+                e = cudaMemcpyAsync(d + lo * each, h + lo * each, (size_t)nc * each * 8, cudaMemcpyHostToDevice, st);
+        };
+        h2d(dA, A_host, strideA, nn);
+        h2d(dB, B_host, strideB, nm);
+        h2d(dQ, Q_host, strideQ, nn);
+        h2d(dR, R_host, strideR, mm);
+        if (e != cudaSuccess) { rc = fail(ctx, QT_ERR_CUDA, "cudaMemcpyAsync (H2D)", cudaGetErrorString(e)); break; }
+        rc = qt_dare_batched(ctx, n, m, nc, strideA ? dA + lo * nn : dA, strideA, strideB ? dB + lo * nm : dB, strideB,
+                             strideQ ? dQ + lo * nn : dQ, strideQ, strideR ? dR + lo * mm : dR, strideR,
+                             dP ? dP + lo * nn : nullptr, dK + lo * nm, dI + lo, dF + lo);
+        if (rc != QT_OK) break;
+        if (K_out_host) e = cudaMemcpyAsync(K_out_host + lo * nm, dK + lo * nm, (size_t)nc * nm * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && P_out_host)
+            e = cudaMemcpyAsync(P_out_host + lo * nn, dP + lo * nn, (size_t)nc * nn * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && iters_out_host)
+            e = cudaMemcpyAsync(iters_out_host + lo, dI + lo, (size_t)nc * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(info_out_host + lo, dF + lo, (size_t)nc * 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail(ctx, QT_ERR_CUDA, "cudaMemcpyAsync (D2H)", cudaGetErrorString(e));
+    }
+    ctx->stream = user_stream;
+    if (n_chunks > 1) {
+        cudaEventRecord(ctx->ev_aux_done, ctx->aux_stream);
+        cudaStreamWaitEvent(user_stream, ctx->ev_aux_done, 0);
+    }
+    cudaError_t es = cudaStreamSynchronize(user_stream);
+    if (rc != QT_OK) return rc;
+    if (es != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "cudaStreamSynchronize", cudaGetErrorString(es));
+    return QT_OK;
+}
+
+// ControllerTuner's candidate batch end to end with HOST buffers (controllers/tuning.py:846-928 for C candidates):
+// diagonal weights in -> design matrices -> C DARE solves -> eps episodes per candidate (seeds seed0 + ep, the same for
+// every candidate, tuning.py:875) -> scores out.  One H2D of (n + 4) doubles per candidate, one D2H of 4 doubles + info.
+extern "C" int qt_sweep_host(qt_context *ctx, const qt_params *params, int32_t n, int64_t C, int64_t eps,
+                             uint64_t seed0, int64_t max_steps, const double *q_host, const double *r_host,
+                             double ctrl_mass, double ctrl_gravity, double *cand_out_host, double *K_out_host,
+                             int32_t *info_out_host) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, params && q_host && r_host && cand_out_host && info_out_host, "null pointer");
+    QT_REQUIRE(ctx, (n == 6 && !params->use_lqi) || (n == 9 && params->use_lqi), "n must be 6 (LQR) or 9 (LQI, use_lqi set)");
+    QT_REQUIRE(ctx, params->controller_type == QT_CTRL_RICCATI, "controller_type must be QT_CTRL_RICCATI");
+    QT_REQUIRE(ctx, C >= 0 && eps >= 1 && eps <= (1 << 20), "bad C / eps");
+    if (C == 0) return QT_OK;
+    std::lock_guard<std::mutex> lock(ctx->host_call_mutex);
+    DeviceGuard guard(ctx->device);
+    const size_t nc = (size_t)C, ne = (size_t)eps, nn = (size_t)n * n;
+    size_t off = 0;
+    auto take = [&](size_t doubles) { size_t o = off; off += ((doubles + 1) & ~(size_t)1) * 8; return o; };
+    const size_t o_q = take(nc * n), o_r = take(nc * 4), oA = take(nn), oB = take((size_t)n * 4), oQ = take(nc * nn),
+                 oR = take(nc * 16), oK = take(nc * 4 * n), oI = take(nc), oF = take(nc), o_seed = take(ne),
+                 o_s0 = take(12 * ne), o_tp = take(12 * ne), o_cand = take(4 * nc);
+    if (int rc0 = ensure_scratch(ctx, off)) return rc0;
+    char *base = reinterpret_cast<char *>(ctx->scratch_dev);
+    auto D = [&](size_t o) { return reinterpret_cast<double *>(base + o); };
+    cudaStream_t st = ctx->stream;
+    QT_CUDA_TRY(ctx, cudaMemcpyAsync(D(o_q), q_host, nc * n * 8, cudaMemcpyHostToDevice, st));
+    QT_CUDA_TRY(ctx, cudaMemcpyAsync(D(o_r), r_host, nc * 4 * 8, cudaMemcpyHostToDevice, st));
+    int rc = qt_build_lqr_systems(ctx, n, C, params->ctrl_dt, ctrl_mass, ctrl_gravity, D(o_q), D(o_r), D(oA), D(oB), D(oQ), D(oR));
+    if (rc) return rc;
+    int32_t *dI = reinterpret_cast<int32_t *>(base + oI), *dF = reinterpret_cast<int32_t *>(base + oF);
+    rc = qt_dare_batched(ctx, n, 4, C, D(oA), 0, D(oB), 0, D(oQ), (int64_t)nn, D(oR), 16, nullptr, D(oK), dI, dF);
+    if (rc) return rc;
+    uint64_t *seeds = reinterpret_cast<uint64_t *>(base + o_seed);
+    rc = qt_fill_seeds(ctx, seeds, eps, seed0);
+    if (rc) return rc;
+    rc = qt_reset_batched(ctx, params, seeds, eps, nullptr, D(o_s0), D(o_tp));
+    if (rc) return rc;
+    rc = qt_rollout_sweep(ctx, params, C, eps, max_steps, D(o_s0), D(o_tp), D(oK), n, D(o_cand), nullptr, nullptr);
+    if (rc) return rc;
+    QT_CUDA_TRY(ctx, cudaMemcpyAsync(cand_out_host, D(o_cand), 4 * nc * 8, cudaMemcpyDeviceToHost, st));
+    QT_CUDA_TRY(ctx, cudaMemcpyAsync(info_out_host, dF, nc * 4, cudaMemcpyDeviceToHost, st));
+    if (K_out_host) QT_CUDA_TRY(ctx, cudaMemcpyAsync(K_out_host, D(oK), nc * 4 * n * 8, cudaMemcpyDeviceToHost, st));
+    QT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return QT_OK;
 }
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/qtrack.h"
 
 struct qt_context {
@@ -17,9 +19,14 @@ struct qt_context {
     // scratch owned by the library (host-buffer entry points only; never handed to the caller)
     void *scratch_dev;
     size_t scratch_bytes;
+    void *sweep_scratch_dev;  // qt_rollout_sweep: metric rows nobody asked for, when the fused reduction cannot be used
+    size_t sweep_scratch_bytes;
     void *partials_dev;       // qt_reduce_summary block partials (partials_cap x 16 doubles)
     int partials_cap;
     char err[512];
+    // The *_host entry points swap `stream` between two lanes and share scratch_dev: they serialise on this mutex.
+    // The *_dev entry points are not locked (they only enqueue on `stream`): use one context per host thread.
+    std::mutex host_call_mutex;
 };
 
 namespace qt {
@@ -46,6 +53,21 @@ inline int check_launch(qt_context *ctx, const char *what) {
     do {                                                               \
         if (!(cond)) return qt::fail((ctx), QT_ERR_ARG, "invalid argument", msg); \
     } while (0)
+
+// Grow-only device scratch of the host-buffer entry points (caller holds host_call_mutex).
+inline int ensure_scratch(qt_context *ctx, size_t total) {
+    if (ctx->scratch_bytes >= total) return QT_OK;
+    if (ctx->scratch_dev) {
+        cudaError_t e = cudaFree(ctx->scratch_dev);
+        if (e != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "cudaFree(scratch)", cudaGetErrorString(e));
+    }
+    ctx->scratch_dev = nullptr;
+    ctx->scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->scratch_dev, total);
+    if (e != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "cudaMalloc(scratch)", cudaGetErrorString(e));
+    ctx->scratch_bytes = total;
+    return QT_OK;
+}
 
 struct DeviceGuard {
     int prev;

@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(kEnvThreads)
     for (int i = 0; i < n_normal; i++) out[(int64_t)(n_uniform + i) * E + e] = rng_standard_normal(g);
 }
 
+// seeds[i] = seed0 + i: Evaluator.evaluate's base_seed + i (eval.py:200) / the tuner's seed + ep (tuning.py:875)
+__global__ void __launch_bounds__(kEnvThreads) fill_seeds_kernel(uint64_t *__restrict__ seeds, int64_t E, uint64_t seed0) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) seeds[e] = seed0 + (uint64_t)e;
+}
+
 // ------------------------------------------------------------------------------ observe ---
 template <int MOTION>
 __device__ __forceinline__ void observe_one(const qt_params &P, int64_t E, int64_t e,
@@ -349,6 +355,15 @@ extern "C" int qt_rng_probe(qt_context *ctx, const uint64_t *seeds_dev, int64_t 
     DeviceGuard guard(ctx->device);
     rng_probe_kernel<<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(seeds_dev, E, n_uniform, n_normal, out_dev);
     return check_launch(ctx, "rng_probe_kernel");
+}
+
+extern "C" int qt_fill_seeds(qt_context *ctx, uint64_t *seeds_out_dev, int64_t E, uint64_t seed0) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, seeds_out_dev && E >= 0, "bad argument");
+    if (E == 0) return QT_OK;
+    DeviceGuard guard(ctx->device);
+    fill_seeds_kernel<<<grid_for(E), kEnvThreads, 0, ctx->stream>>>(seeds_out_dev, E, seed0);
+    return check_launch(ctx, "fill_seeds_kernel");
 }
 
 extern "C" int qt_observe_batched(qt_context *ctx, const qt_params *params, int64_t E,

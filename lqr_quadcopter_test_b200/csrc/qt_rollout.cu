@@ -16,6 +16,7 @@
 #include <type_traits>
 
 #include "qt_common.cuh"
+#include "qt_npsum.cuh"
 #include "qt_step.cuh"
 
 namespace qt {
@@ -39,6 +40,12 @@ struct RolloutArgs {
     double *metrics, *ctrl_state, *final_state, *traj;
     float *feat, *actf;
     int traj_stride, traj_slots, data_stride, data_slots;
+    // candidate sweep (qt_rollout_sweep): episode e starts from initial condition e % ic_period (0 = its own),
+    // and each block reduces the eps episodes of its candidates to scores[4][n_cand] (NULL = no fused reduction)
+    int64_t ic_period;
+    double *scores;
+    int64_t n_cand;
+    int eps;
 };
 
 // Per-thread values that are touched once per step (metric accumulators, target-pattern
@@ -80,14 +87,16 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         for (int i = threadIdx.x; i < n; i += T) sK[i] = src[i];
         __syncthreads();
     }
-    if (chain_id >= A.n_chains) return;
+    // threads past the last chain fall through with an empty episode range: the score epilogue below
+    // synchronises the whole block
+    const bool active = chain_id < A.n_chains;
 
     const bool euler = FULL && (P.integrator == QT_INTEGRATOR_EULER);
 
     double integ[3] = {0.0, 0.0, 0.0};
     int saturations = 0;
     double last_time = __longlong_as_double(0x7ff8000000000000LL);  // PID: time of the previous call, NaN = none
-    if (A.ctrl_state && A.chain > 1) {  // the controller object's state at the time of the call
+    if (A.ctrl_state && A.chain > 1 && active) {  // the controller object's state at the time of the call
 #pragma unroll
         for (int i = 0; i < 3; i++) integ[i] = A.ctrl_state[(int64_t)i * A.n_chains + chain_id];
         if (CTRL == CK_PID)
@@ -96,16 +105,19 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             saturations = (int)A.ctrl_state[3 * A.n_chains + chain_id];
     }
 
-    const int64_t first = chain_id * A.chain;
+    const int64_t first = active ? chain_id * A.chain : E;
     int64_t last = first + A.chain;
     if (last > E) last = E;
+    // initial conditions: [12][E] indexed by the episode, or (sweep) [12][ic_period] shared by all candidates
+    const int64_t ic_E = A.ic_period > 0 ? A.ic_period : E;
 
     for (int64_t e = first; e < last; e++) {
+        const int64_t e_ic = A.ic_period > 0 ? e % A.ic_period : e;
         double s[12];
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = A.state0[(int64_t)i * E + e];
+        for (int i = 0; i < 12; i++) s[i] = A.state0[(int64_t)i * ic_E + e_ic];
         TargetGen<MOTION, T> tg;
-        tg.load(cold + CR_TARGET * T, A.tparams, E, e);
+        tg.load(cold + CR_TARGET * T, A.tparams, ic_E, e_ic);
         const int64_t grp = e / A.k_stride;
         const double *Kp = A.k_in_smem ? (sK + (grp - g0) * 4 * KC) : (A.K + grp * 4 * KC);
         const double *ffg = (FULL && A.ff) ? A.ff + grp * 6 : nullptr;
@@ -318,6 +330,18 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         const double n = (double)step;
         const double env_ratio = step > 0 ? (double)env_on / n : 0.0;
         const double met_ratio = step > 0 ? (double)met_on / n : 0.0;
+        const double met_success =
+            (step > 0 && t >= P.crit_min_episode_duration && met_ratio >= P.crit_min_on_target_ratio) ? 1.0 : 0.0;
+        if (A.scores) {
+            // what reduce_scores_kernel would read back from the metric rows (tuning.py:908-917), parked in
+            // this thread's column of the cold tile for the block-level reduction after the loop
+            const double mean_err = step > 0 ? cold[CR_SUM_ERR * T] / n : 0.0;
+            // (rows of the target-pattern trig: free once the episode is over, and chain == 1 here)
+            cold[(CR_TARGET_TRIG + 0) * T] = met_ratio;
+            cold[(CR_TARGET_TRIG + 1) * T] = mean_err;
+            cold[(CR_TARGET_TRIG + 2) * T] = met_success;
+        }
+        if (A.metrics) {
         double *m = A.metrics + e;
         m[(int64_t)QT_M_STEPS * E] = n;
         m[(int64_t)QT_M_FINAL_TIME * E] = t;
@@ -331,23 +355,44 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
         m[(int64_t)QT_M_MAX_OVERSHOOT * E] = ov_max;
         m[(int64_t)QT_M_ENV_SUCCESS * E] =
             (t >= P.env_min_episode_duration && env_ratio >= P.env_min_on_target_ratio) ? 1.0 : 0.0;
-        m[(int64_t)QT_M_MET_SUCCESS * E] =
-            (step > 0 && t >= P.crit_min_episode_duration && met_ratio >= P.crit_min_on_target_ratio)
-                ? 1.0
-                : 0.0;
+        m[(int64_t)QT_M_MET_SUCCESS * E] = met_success;
         m[(int64_t)QT_M_TERMINATION * E] = (double)term;
         m[(int64_t)QT_M_VIOLATIONS * E] = (double)violations;
         m[(int64_t)QT_M_SATURATIONS * E] = (double)saturations;
         m[(int64_t)QT_M_FINAL_ERR * E] = err_post;
+        }
         if (A.final_state) {
 #pragma unroll
             for (int i = 0; i < 12; i++) A.final_state[(int64_t)i * E + e] = s[i];
         }
     }
-    if (A.ctrl_state) {
+    if (A.ctrl_state && active) {
 #pragma unroll
         for (int i = 0; i < 3; i++) A.ctrl_state[(int64_t)i * A.n_chains + chain_id] = integ[i];
         A.ctrl_state[3 * A.n_chains + chain_id] = CTRL == CK_PID ? last_time : (double)saturations;
+    }
+    if (A.scores) {
+        // ControllerTuner._evaluate_config's aggregation (tuning.py:912-926) fused into the rollout: the host
+        // guarantees chain == 1 and eps | 128, so a block holds whole candidates; the first thread of each
+        // candidate sums its eps episodes in numpy's pairwise order (qt_npsum.cuh) -> bit-identical to
+        // qt_reduce_scores on the metric rows, which then never have to be written (16 x 8 B per episode).
+        __syncthreads();
+        const int eps = A.eps;
+        if (active && (threadIdx.x % eps) == 0) {
+            const double *col = smem + threadIdx.x;
+            auto ratio_f = [=](int64_t k) { return col[(CR_TARGET_TRIG + 0) * T + k]; };
+            auto merr_f = [=](int64_t k) { return col[(CR_TARGET_TRIG + 1) * T + k]; };
+            auto succ_f = [=](int64_t k) { return col[(CR_TARGET_TRIG + 2) * T + k]; };
+            const double ne = (double)eps;
+            const double mean_on = np_sum(ratio_f, eps) / ne;
+            const double mean_err = np_sum(merr_f, eps) / ne;
+            const double sr = np_sum(succ_f, eps) / ne;
+            const int64_t c = chain_id / eps, C = A.n_cand;
+            A.scores[0 * C + c] = __dadd_rn(mean_on, -__dmul_rn(0.1, mean_err));  // mean_on - 0.1 * mean_err, unfused
+            A.scores[1 * C + c] = mean_on;
+            A.scores[2 * C + c] = mean_err;
+            A.scores[3 * C + c] = sr;
+        }
     }
 }
 
@@ -380,59 +425,27 @@ static cudaError_t launch_motion(const qt_params &P, const RolloutArgs &A, size_
 
 }  // namespace qt
 
-extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
-                          int64_t chain, const double *state0_dev, const double *tparams_dev,
-                          const double *K_dev, int32_t k_cols, int64_t k_stride,
-                          double *metrics_out_dev, double *ctrl_state_io_dev,
-                          double *final_state_out_dev, double *traj_out_dev, int64_t traj_stride,
-                          int64_t traj_slots,
-                          float *feat_out_dev, float *act_out_dev, int64_t data_stride,
-                          int64_t data_slots, const double *ff_gains_dev) {
+// Shared tail of qt_rollout / qt_rollout_sweep: argument checks, K staging, kernel-mode selection, launch.
+// A arrives with the caller-specific fields (ic_period, scores, n_cand, eps, metrics, ...) already set.
+static int rollout_launch(qt_context *ctx, const qt_params *params, qt::RolloutArgs &A, int32_t k_cols) {
     using namespace qt;
-    if (!ctx) return QT_ERR_ARG;
-    QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
-    QT_REQUIRE(ctx, E >= 0 && max_steps >= 0 && max_steps < (1ll << 31), "bad E / max_steps");
+    QT_REQUIRE(ctx, A.E >= 0 && A.max_steps >= 0, "bad E / max_steps");
     QT_REQUIRE(ctx, k_cols == expected_k_cols(*params), "k_cols must be 6 (LQR), 9 (LQI) or 3 (PID)");
-    QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(K_dev) & 15) == 0, "K must be 16-byte aligned");
+    QT_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(A.K) & 15) == 0, "K must be 16-byte aligned");
     QT_REQUIRE(ctx, params->motion_type >= 0 && params->motion_type <= QT_MOTION_FIGURE8, "motion_type");
-    QT_REQUIRE(ctx, (feat_out_dev == nullptr) == (act_out_dev == nullptr), "feat/act must come together");
-    if (E == 0) return QT_OK;
-    if (chain < 1) chain = 1;
-    if (k_stride < 1) k_stride = 1;
-    if (traj_stride < 1) traj_stride = 1;
-    if (data_stride < 1) data_stride = 1;
-    QT_REQUIRE(ctx, traj_stride < (1ll << 31) && data_stride < (1ll << 31) &&
-                        traj_slots < (1ll << 31) && data_slots < (1ll << 31), "log strides/slots");
+    QT_REQUIRE(ctx, (A.feat == nullptr) == (A.actf == nullptr), "feat/act must come together");
+    if (A.E == 0) return QT_OK;
+    A.n_chains = (A.E + A.chain - 1) / A.chain;
+    if (!params->feedforward_enabled) A.ff = nullptr;
 
-    RolloutArgs A;
-    A.E = E;
-    A.chain = chain;
-    A.n_chains = (E + chain - 1) / chain;
-    A.k_stride = k_stride;
-    A.max_steps = (int)max_steps;
-    A.state0 = state0_dev;
-    A.tparams = tparams_dev;
-    A.K = K_dev;
-    A.ff = params->feedforward_enabled ? ff_gains_dev : nullptr;
-    A.metrics = metrics_out_dev;
-    A.ctrl_state = ctrl_state_io_dev;
-    A.final_state = final_state_out_dev;
-    A.traj = traj_out_dev;
-    A.feat = feat_out_dev;
-    A.actf = act_out_dev;
-    A.traj_stride = (int)traj_stride;
-    A.traj_slots = (int)traj_slots;
-    A.data_stride = (int)data_stride;
-    A.data_slots = (int)data_slots;
-
-    // K staging: with one episode per thread a block needs at most ceil(T / k_stride) + 1 groups
     // the env's range checks can only trigger if the controller is allowed to exceed the env's limits
     A.env_bounds_check = !(params->ctrl_min_thrust >= params->min_thrust && params->ctrl_max_thrust <= params->max_thrust &&
                            params->ctrl_max_rate <= params->max_angular_rate && params->ctrl_max_rate >= 0.0);
+    // K staging: with one episode per thread a block needs at most ceil(T / k_stride) + 1 groups
     A.k_in_smem = 0;
     A.k_smem_doubles = 0;
-    if (chain == 1) {
-        int64_t groups = (kRolloutThreads + k_stride - 1) / k_stride + 1;
+    if (A.chain == 1) {
+        int64_t groups = (kRolloutThreads + A.k_stride - 1) / A.k_stride + 1;
         size_t doubles = ((size_t)groups * 4 * k_cols + 1) & ~(size_t)1;  // keep the cold tile 16-byte aligned
         if (doubles * sizeof(double) <= 24 * 1024) {
             A.k_in_smem = 1;
@@ -441,8 +454,8 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     }
     // the per-thread cold-state tile (kColdRows x 128 doubles = 17 KB) + staged gains
     const size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
-    const bool needs_full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 || traj_out_dev != nullptr;
-    const int full = needs_full ? 1 : (feat_out_dev != nullptr ? 2 : 0);   // kernel MODE
+    const bool needs_full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 || A.traj != nullptr;
+    const int full = needs_full ? 1 : (A.feat != nullptr ? 2 : 0);   // kernel MODE
 
     DeviceGuard guard(ctx->device);
     cudaError_t err;
@@ -456,4 +469,94 @@ extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, i
     if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "rollout_kernel launch", cudaGetErrorString(err));
     ctx->launches += 1;
     return QT_OK;
+}
+
+extern "C" int qt_rollout(qt_context *ctx, const qt_params *params, int64_t E, int64_t max_steps,
+                          int64_t chain, const double *state0_dev, const double *tparams_dev,
+                          const double *K_dev, int32_t k_cols, int64_t k_stride,
+                          double *metrics_out_dev, double *ctrl_state_io_dev,
+                          double *final_state_out_dev, double *traj_out_dev, int64_t traj_stride,
+                          int64_t traj_slots,
+                          float *feat_out_dev, float *act_out_dev, int64_t data_stride,
+                          int64_t data_slots, const double *ff_gains_dev) {
+    using namespace qt;
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev && metrics_out_dev, "null pointer");
+    QT_REQUIRE(ctx, E >= 0 && max_steps >= 0 && max_steps < (1ll << 31), "bad E / max_steps");
+    if (chain < 1) chain = 1;
+    if (k_stride < 1) k_stride = 1;
+    if (traj_stride < 1) traj_stride = 1;
+    if (data_stride < 1) data_stride = 1;
+    QT_REQUIRE(ctx, traj_stride < (1ll << 31) && data_stride < (1ll << 31) &&
+                        traj_slots < (1ll << 31) && data_slots < (1ll << 31), "log strides/slots");
+    RolloutArgs A{};
+    A.E = E;
+    A.chain = chain;
+    A.k_stride = k_stride;
+    A.max_steps = (int)max_steps;
+    A.state0 = state0_dev;
+    A.tparams = tparams_dev;
+    A.K = K_dev;
+    A.ff = ff_gains_dev;
+    A.metrics = metrics_out_dev;
+    A.ctrl_state = ctrl_state_io_dev;
+    A.final_state = final_state_out_dev;
+    A.traj = traj_out_dev;
+    A.feat = feat_out_dev;
+    A.actf = act_out_dev;
+    A.traj_stride = (int)traj_stride;
+    A.traj_slots = (int)traj_slots;
+    A.data_stride = (int)data_stride;
+    A.data_slots = (int)data_slots;
+    return rollout_launch(ctx, params, A, k_cols);
+}
+
+// ControllerTuner's candidate batch in one launch (controllers/tuning.py:846-928): C candidates x eps episodes,
+// episode (c, ep) = global index c * eps + ep starts from initial condition ep under gain K[c].
+extern "C" int qt_rollout_sweep(qt_context *ctx, const qt_params *params, int64_t C, int64_t eps,
+                                int64_t max_steps, const double *state0_dev, const double *tparams_dev,
+                                const double *K_dev, int32_t k_cols, double *cand_out_dev,
+                                double *metrics_out_dev, const double *ff_gains_dev) {
+    using namespace qt;
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, params && state0_dev && tparams_dev && K_dev, "null pointer");
+    QT_REQUIRE(ctx, cand_out_dev || metrics_out_dev, "cand_out and metrics_out are both NULL");
+    QT_REQUIRE(ctx, C >= 0 && eps >= 1 && max_steps >= 0 && max_steps < (1ll << 31), "bad C / eps / max_steps");
+    QT_REQUIRE(ctx, C <= (1ll << 40) / eps, "C * eps too large");
+    if (C == 0) return QT_OK;
+    RolloutArgs A{};
+    A.E = C * eps;
+    A.chain = 1;                // controller.reset() before every episode (tuning.py:879)
+    A.k_stride = eps;
+    A.max_steps = (int)max_steps;
+    A.state0 = state0_dev;
+    A.tparams = tparams_dev;
+    A.K = K_dev;
+    A.ff = ff_gains_dev;
+    A.traj_stride = A.data_stride = 1;
+    A.ic_period = eps;
+    A.n_cand = C;
+    A.eps = (int)eps;
+    // the fused reduction needs whole candidates per 128-episode block; other episode counts write the metric rows
+    // (into library scratch when the caller does not want them) and reduce with qt_reduce_scores
+    const bool fused = cand_out_dev && eps <= kRolloutThreads && (kRolloutThreads % eps) == 0;
+    A.scores = fused ? cand_out_dev : nullptr;
+    A.metrics = metrics_out_dev;
+    if (!fused && !metrics_out_dev) {
+        DeviceGuard guard(ctx->device);
+        const size_t need = (size_t)QT_METRICS_DIM * (size_t)A.E * sizeof(double);
+        if (ctx->sweep_scratch_bytes < need) {
+            if (ctx->sweep_scratch_dev) QT_CUDA_TRY(ctx, cudaFree(ctx->sweep_scratch_dev));
+            ctx->sweep_scratch_dev = nullptr;
+            ctx->sweep_scratch_bytes = 0;
+            QT_CUDA_TRY(ctx, cudaMalloc(&ctx->sweep_scratch_dev, need));
+            ctx->sweep_scratch_bytes = need;
+        }
+        A.metrics = reinterpret_cast<double *>(ctx->sweep_scratch_dev);
+    }
+    const double *metrics_for_reduce = A.metrics;
+    int rc = rollout_launch(ctx, params, A, k_cols);
+    if (rc != QT_OK) return rc;
+    if (cand_out_dev && !fused) rc = qt_reduce_scores(ctx, metrics_for_reduce, C, eps, cand_out_dev);
+    return rc;
 }

@@ -41,6 +41,18 @@ def init_process_group(backend: str | None = None) -> tuple[int, int, int]:
     return rank, size, local
 
 
+def is_primary() -> bool:
+    """True on the rank that writes files (rank 0; always true for a single process)."""
+    return world()[0] == 0
+
+
+def barrier() -> None:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def shard_range(total: int, rank: int, size: int) -> tuple[int, int]:
     """Contiguous block [lo, hi) of ``total`` units owned by ``rank`` (sizes differ by at most 1)."""
     base, rem = divmod(int(total), int(size))
@@ -60,36 +72,73 @@ def all_gather_vectors(vec, device=None):
     return parts
 
 
-def reduce_summary_across_ranks(local_sums, local_offset: int, criteria=None):
+def reduce_summary_across_ranks(local_sums, local_offset: int, criteria=None, extra=None):
     """All ranks contribute the 16 sums of their shard (qt_reduce_summary) and the global index of
     their first episode; every rank returns the same EvaluationSummary (without per-episode
-    objects — those stay on the rank that owns them)."""
+    objects — those stay on the rank that owns them).  ``extra`` (a small 1-D float64 tensor of the same length on
+    every rank) rides along in the same all_gather; then the second return value is a dict
+    ``{"sums": merged, "extra": [rank 0's, rank 1's, ...]}`` instead of the merged sums."""
     import torch
 
-    payload = torch.cat([local_sums.reshape(-1).to(torch.float64),
-                         torch.tensor([float(local_offset)], dtype=torch.float64, device=local_sums.device)])
-    parts = [p.cpu().numpy() for p in all_gather_vectors(payload)]
+    dev = local_sums.device
+    parts_in = [local_sums.reshape(-1).to(torch.float64), torch.tensor([float(local_offset)], dtype=torch.float64, device=dev)]
+    if extra is not None:
+        parts_in.append(extra.reshape(-1).to(torch.float64).to(dev))
+    parts = [p.cpu().numpy() for p in all_gather_vectors(torch.cat(parts_in))]
     merged = merge_summary_sums([p[:16] for p in parts], [int(p[16]) for p in parts])
-    return summary_from_sums(merged, criteria, []), merged
+    summary = summary_from_sums(merged, criteria, [])
+    if extra is None:
+        return summary, merged
+    return summary, {"sums": merged, "extra": [p[17:] for p in parts]}
+
+
+def evaluation_shard_plan(num_episodes: int, rank: int, size: int, carries_over: bool) -> tuple[int, int, int]:
+    """(lo, hi, chain) of the episodes rank ``rank`` evaluates.
+
+    Episodes are independent — and shard contiguously — unless the controller carries state from one episode into
+    the next: ``Evaluator.evaluate`` never resets the controller (eval.py:198-213), so an LQI integrator (or a PID
+    integral with a non-zero limit) makes the episodes of one evaluation a serial chain.  That chain cannot be cut:
+    rank 0 runs all of it in one GPU thread (chain = num_episodes), the other ranks contribute an empty shard, and
+    the final reduction hands every rank the same summary."""
+    if carries_over:
+        return (0, int(num_episodes), max(int(num_episodes), 2)) if rank == 0 else (0, 0, 1)
+    lo, hi = shard_range(num_episodes, rank, size)
+    return lo, hi, 1
 
 
 def evaluate_sharded(evaluator, num_episodes: int, base_seed: int = 42, max_steps: int | None = None):
-    """Evaluator.evaluate over all ranks: rank r evaluates episodes [lo, hi) with seeds
-    base_seed + index, then the 16-sum vectors are merged.  Returns (summary, local_metrics_host)."""
+    """Evaluator.evaluate over all ranks: rank r evaluates its shard of the episodes (seeds base_seed + index) and
+    the 16-sum vectors are merged.  Honours ``evaluator.reset_controller_between_episodes`` exactly like the
+    single-process ``Evaluator.evaluate``: a state-carrying controller that is not reset runs as one serial chain on
+    rank 0 (see evaluation_shard_plan) and its final state is written back to the controller object on every rank.
+    Returns (summary, local_metrics [16, hi - lo])."""
     import torch
 
     from . import _lib
     from .eval import rollout_device
 
     rank, size, _ = world()
-    lo, hi = shard_range(num_episodes, rank, size)
+    ctrl = evaluator.controller
+    carries = bool(ctrl.carries_state()) and not evaluator.reset_controller_between_episodes
+    lo, hi, chain = evaluation_shard_plan(num_episodes, rank, size, carries)
     ctx = _lib.get_context()
-    seeds = torch.arange(lo, hi, dtype=torch.int64, device=ctx.device) + int(base_seed)
-    out = rollout_device(evaluator.controller, evaluator.env_config, evaluator.criteria, seeds, max_steps, ctx=ctx)
-    sums = torch.zeros(16, dtype=torch.float64, device=ctx.device)
-    ctx.reduce_summary(out["metrics"], hi - lo, sums)
-    summary, _ = reduce_summary_across_ranks(sums, lo, evaluator.criteria)
-    return summary, out["metrics"]
+    f64 = dict(dtype=torch.float64, device=ctx.device)
+    sums = torch.zeros(16, **f64)
+    state = torch.zeros(4, **f64)
+    metrics = torch.empty((16, 0), **f64)
+    if hi > lo:
+        seeds = torch.arange(lo, hi, dtype=torch.int64, device=ctx.device) + int(base_seed)
+        st = evaluator._ctrl_state_in((hi - lo + chain - 1) // chain) if carries else None
+        out = rollout_device(ctrl, evaluator.env_config, evaluator.criteria, seeds, max_steps, chain=chain,
+                             ctrl_state=st, ctx=ctx)
+        metrics = out["metrics"]
+        ctx.reduce_summary(metrics, hi - lo, sums)
+        if carries:
+            state = st[:, 0].contiguous()
+    summary, merged = reduce_summary_across_ranks(sums, lo, evaluator.criteria, extra=state if carries else None)
+    if carries:
+        ctrl.load_state_vector(merged["extra"][0], True)
+    return summary, metrics
 
 
 def teacher_dataset_sharded(controller, env_config=None, num_episodes: int = 1 << 22, base_seed: int = 42,
@@ -107,9 +156,10 @@ def teacher_dataset_sharded(controller, env_config=None, num_episodes: int = 1 <
 
 
 def gather_candidate_scores(local_cand, total_candidates: int):
-    """Tuning: each rank scored candidates [lo, hi); gather the [4, C_local] rows into [4, C] on every
-    rank (an all_gather of <= 2 MiB for 65 536 candidates).  Shards may differ by one candidate, so
-    rows are padded to the largest shard before the collective."""
+    """Tuning: each rank scored candidates [lo, hi); gather the [R, C_local] rows (R = 4 score rows, optionally
+    followed by the candidates' parameter rows) into [R, C] on every rank — an all_gather of <= 2 MiB for the scores
+    of 65 536 candidates.  Shards may differ by one candidate, so rows are padded to the largest shard before the
+    collective."""
     import torch
     import torch.distributed as dist
 
@@ -118,23 +168,43 @@ def gather_candidate_scores(local_cand, total_candidates: int):
     size = dist.get_world_size()
     widths = [shard_range(total_candidates, r, size) for r in range(size)]
     wmax = max(hi - lo for lo, hi in widths)
-    pad = torch.zeros((4, wmax), dtype=local_cand.dtype, device=local_cand.device)
+    rows = local_cand.shape[0]
+    pad = torch.zeros((rows, wmax), dtype=local_cand.dtype, device=local_cand.device)
     pad[:, : local_cand.shape[1]] = local_cand
-    parts = [torch.empty_like(pad) for _ in range(size)]
-    dist.all_gather(parts, pad)
-    return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, widths)], dim=1)
+    out = torch.empty((size * rows, wmax), dtype=local_cand.dtype, device=local_cand.device)
+    dist.all_gather_into_tensor(out, pad)        # rank r's block = rows [r * rows, (r + 1) * rows)
+    out = out.reshape(size, rows, wmax)
+    return torch.cat([out[r, :, : hi - lo] for r, (lo, hi) in enumerate(widths)], dim=1)
 
 
-def evaluate_candidates_sharded(tuner, configs: list[dict]) -> tuple[list[float], list[dict]]:
-    """ControllerTuner.evaluate_configs over all ranks (BASELINE config 4: the candidates of a Q/R sweep,
-    each with its DARE solve and its evaluation episodes, split contiguously over the GPUs).  Rank r scores
-    candidates [lo, hi) — every candidate sees the same episode seeds wherever it runs (tuning.py:875), so
-    the scores do not depend on the partition — and one all_gather of the [4, C_local] score rows gives
-    every rank the full lists, in candidate order."""
+def _collective_device():
     import torch
     import torch.distributed as dist
 
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_candidate_rows(local_rows: np.ndarray, total_candidates: int) -> np.ndarray:
+    """numpy front of gather_candidate_scores: [R, C_local] in, [R, C] out (same on every rank)."""
+    import torch
+
+    t = torch.as_tensor(np.ascontiguousarray(local_rows), dtype=torch.float64, device=_collective_device())
+    return gather_candidate_scores(t, total_candidates).cpu().numpy()
+
+
+def evaluate_candidates_sharded(tuner, configs: list[dict]) -> tuple[list[float], list[dict]]:
+    """ControllerTuner.evaluate_configs over all ranks for candidates given as dictionaries (grid search, resumed
+    runs): the same list on every rank, rank r scores candidates [lo, hi) — every candidate sees the same episode
+    seeds wherever it runs (tuning.py:875), so the scores do not depend on the partition — and one all_gather of the
+    [4, C_local] score rows gives every rank the full lists, in candidate order.  (Random search does not come
+    through here: ControllerTuner.sweep draws and scores arrays.)"""
+    import torch.distributed as dist
+
     rank, size, _ = world()
+    if not configs:
+        return [], []          # nothing to score: no collective either
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return tuner.evaluate_configs(configs)
     C = len(configs)
@@ -143,13 +213,18 @@ def evaluate_candidates_sharded(tuner, configs: list[dict]) -> tuple[list[float]
     eps = metrics[0]["episodes_evaluated"] if metrics else int(tuner.config.evaluation_episodes)
     rows = np.array([scores, [m["mean_on_target_ratio"] for m in metrics], [m["mean_tracking_error"] for m in metrics],
                      [m["success_rate"] for m in metrics]], dtype=np.float64).reshape(4, hi - lo)
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    full = gather_candidate_scores(torch.as_tensor(rows, device=dev), C).cpu().numpy()
+    full = gather_candidate_rows(rows, C)
     out = [{"mean_on_target_ratio": a, "mean_tracking_error": b, "success_rate": c, "episodes_evaluated": eps}
            for a, b, c in zip(full[1].tolist(), full[2].tolist(), full[3].tolist())]
     return full[0].tolist(), out
 
 
 def argmax_first(scores: np.ndarray) -> int:
-    """Best candidate with the reference's tie rule (strict '>' while scanning, tuning.py:1084)."""
-    return int(np.argmax(scores))
+    """Index of the best candidate with the reference's rule — a scan that replaces the incumbent only on a
+    strict '>' (tuning.py:1084), so the first of equal scores wins and NaN scores never do (np.argmax would return
+    the first NaN).  -1 if there is no comparable score at all."""
+    scores = np.asarray(scores, dtype=np.float64)
+    ok = ~np.isnan(scores)
+    if not ok.any():
+        return -1
+    return int(np.argmax(np.where(ok, scores, -np.inf)))

@@ -198,6 +198,80 @@ def _validate_path(path: Path) -> None:
 _Q_POS_DEFAULT, _Q_VEL_DEFAULT = [0.0001, 0.0001, 16.0], [0.0036, 0.0036, 4.0]   # riccati_lqr.py:624-625
 _Q_INT_DEFAULT, _R_DEFAULT = [0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0]
 
+# the order in which _generate_random_config draws its parameters (tuning.py:683-735) and their widths
+_PARAM_ORDER = (("kp_pos", 3), ("ki_pos", 3), ("kd_pos", 3), ("ff_velocity_gain", 3), ("ff_acceleration_gain", 3),
+                ("q_pos", 3), ("q_vel", 3), ("r_thrust", 1), ("r_rate", 1), ("r_controls", 4), ("q_int", 3))
+
+
+@dataclass
+class CandidateBlock:
+    """A batch of tuner candidates as ONE array instead of a list of dictionaries: ``values[i]`` holds candidate i's
+    parameters in the reference's draw order, ``spec`` names the columns.  ``config(i)`` rebuilds exactly the
+    dictionary ``_generate_random_config`` would have returned for that candidate."""
+
+    spec: list            # [(name, dim), ...] in column order
+    values: np.ndarray    # float64 [C, sum(dim)]
+    use_lqi: bool = False
+    zero_q_int: bool = False   # use_lqi without a q_int range: q_int = [0, 0, 0] (tuning.py:727-733)
+
+    def __len__(self) -> int:
+        return int(self.values.shape[0])
+
+    def column(self, name: str):
+        """float64 [C, dim] view of one parameter, or None if it is not part of the search."""
+        at = 0
+        for key, dim in self.spec:
+            if key == name:
+                return self.values[:, at:at + dim]
+            at += dim
+        return None
+
+    @property
+    def feedforward_enabled(self) -> bool:
+        return any(k in ("ff_velocity_gain", "ff_acceleration_gain") for k, _ in self.spec)
+
+    def config(self, i: int) -> dict:
+        row, cfg, at = self.values[i], {}, 0
+        for key, dim in self.spec:
+            cfg[key] = float(row[at]) if dim == 1 else [float(v) for v in row[at:at + dim]]
+            if key in ("ff_velocity_gain", "ff_acceleration_gain"):
+                cfg["feedforward_enabled"] = True
+            if key == "q_int":
+                cfg["use_lqi"] = True
+            at += dim
+        if self.zero_q_int:
+            cfg["use_lqi"] = True
+            cfg["q_int"] = [0.0, 0.0, 0.0]
+        return cfg
+
+    def configs(self) -> list[dict]:
+        return [self.config(i) for i in range(len(self))]
+
+    def slice(self, lo: int, hi: int) -> "CandidateBlock":
+        return CandidateBlock(self.spec, self.values[lo:hi], self.use_lqi, self.zero_q_int)
+
+    @classmethod
+    def from_configs(cls, configs: list[dict]) -> "CandidateBlock | None":
+        """Pack dictionaries that all carry the same keys (what the generators produce) into one array; None if they
+        differ in their key sets or in a non-searched entry (those batches are evaluated one by one)."""
+        first = configs[0]
+        keys = [(k, d) for k, d in _PARAM_ORDER if k in first]
+        searched = {k for k, _ in keys}
+        fixed = {k: first[k] for k in first if k not in searched}
+        for c in configs:
+            if c.keys() != first.keys():
+                return None
+            for k, v in fixed.items():
+                same = c[k] == v
+                if not (bool(np.all(same)) if not isinstance(same, bool) else same):
+                    return None
+        try:
+            cols = [np.asarray([c[k] for c in configs], dtype=np.float64).reshape(len(configs), d) for k, d in keys]
+        except (ValueError, TypeError):
+            return None
+        values = np.concatenate(cols, axis=1) if cols else np.zeros((len(configs), 0))
+        return cls(keys, np.ascontiguousarray(values), bool(first.get("use_lqi", False)), False)
+
 
 class ControllerTuner:
     """tuning.py:581-1442 for the Riccati-LQR / LQI (and heuristic LQR) controllers."""
@@ -223,6 +297,43 @@ class ControllerTuner:
         self._cma_param_spec: list[tuple[str, int, tuple]] = []
 
     # -- candidate generation: host, identical RNG consumption to tuning.py:662-735 -----------------
+    def _active_spec(self) -> list[tuple[str, int, np.ndarray, np.ndarray]]:
+        sp, out = self.config.search_space, []
+        for key, dim in _PARAM_ORDER:
+            rng_def = getattr(sp, key + "_range")
+            if rng_def is not None:
+                lo, hi = (np.asarray(v, dtype=np.float64).reshape(dim) for v in rng_def)
+                out.append((key, dim, lo, hi))
+        return out
+
+    def sample_candidates(self, count: int, lo: int = 0, hi: int | None = None) -> CandidateBlock:
+        """``count`` random candidates in one call, consuming ``self.rng`` exactly like ``count`` calls of
+        ``_generate_random_config`` (tuning.py:683-735): every parameter there is one scalar ``rng.uniform(lo, hi)``,
+        i.e. ``lo + (hi - lo) * next_double`` with one generator step per draw, taken in a fixed order — so one
+        ``rng.uniform(lo_row, hi_row, size=(count, k))`` (numpy fills it row by row with the same C routine) yields
+        the same bits, 65 536 x 14 draws in ~10 ms instead of 1 s of Python calls.
+
+        ``lo, hi`` select candidates [lo, hi) of the ``count`` (a rank's shard): the generator is advanced past the
+        others (PCG64.advance, one step per draw), so the rows — and the generator's final state — are what the full
+        draw would have given."""
+        hi = count if hi is None else hi
+        spec = self._active_spec()
+        k = sum(d for _, d, _, _ in spec)
+        sp = self.config.search_space
+        zero_q_int = bool(sp.use_lqi and sp.q_int_range is None)
+        use_lqi = bool(sp.use_lqi or sp.q_int_range is not None)
+        if k == 0:
+            return CandidateBlock([], np.zeros((hi - lo, 0)), use_lqi, zero_q_int)
+        lo_row = np.concatenate([l for _, _, l, _ in spec])
+        hi_row = np.concatenate([h for _, _, _, h in spec])
+        bg = self.rng.bit_generator
+        if lo > 0:
+            bg.advance(lo * k)
+        values = self.rng.uniform(lo_row, hi_row, size=(hi - lo, k))
+        if hi < count:
+            bg.advance((count - hi) * k)
+        return CandidateBlock([(n, d) for n, d, _, _ in spec], values, use_lqi, zero_q_int)
+
     def _draw(self, rng_def):
         lo_v, hi_v = rng_def
         return [float(self.rng.uniform(lo, hi)) for lo, hi in zip(lo_v, hi_v)]
@@ -310,7 +421,7 @@ class ControllerTuner:
 
     def _evaluate_config(self, controller_config: dict) -> tuple[float, dict]:
         """tuning.py:846-928 for one candidate (one controller object, hence one DARE)."""
-        scores, metrics = self.evaluate_configs([controller_config])
+        scores, metrics = self._rows_to_lists(np.asarray(self._evaluate_one(controller_config)).reshape(4, 1))
         return scores[0], metrics[0]
 
     @staticmethod
@@ -325,94 +436,135 @@ class ControllerTuner:
         """Score every candidate configuration: returns (scores, metrics dictionaries)."""
         if not configs:
             return [], []
-        if not self._batchable(configs) or any("Q" in c or "R" in c or "K" in c for c in configs):
-            parts = [self._evaluate_batch([c]) for c in configs]
-            return [p[0][0] for p in parts], [p[1][0] for p in parts]
-        scores, metrics = [], []
-        for i in range(0, len(configs), self.max_batch_candidates):
-            s, m = self._evaluate_batch(configs[i:i + self.max_batch_candidates])
-            scores += s
-            metrics += m
-        return scores, metrics
+        block = None
+        if self._batchable(configs) and not any("Q" in c or "R" in c or "K" in c for c in configs):
+            block = CandidateBlock.from_configs(configs)
+        if block is None:
+            parts = [self._evaluate_one(c) for c in configs]
+            rows = np.array([p for p in parts], dtype=np.float64).T.reshape(4, len(configs))
+        else:
+            rows = self.evaluate_block(block, configs)
+        return self._rows_to_lists(rows)
 
-    def _gains_for(self, configs: list[dict], ctx):
-        """Device gains [C, 4, k_cols] for a batch of candidates + the controller prototype that
-        carries the shared (non-tuned) controller parameters."""
-        import torch
+    def _rows_to_lists(self, rows: np.ndarray) -> tuple[list[float], list[dict]]:
+        eps = int(self.config.evaluation_episodes)
+        out = [{"mean_on_target_ratio": a, "mean_tracking_error": b, "success_rate": c_, "episodes_evaluated": eps}
+               for a, b, c_ in zip(rows[1].tolist(), rows[2].tolist(), rows[3].tolist())]
+        return rows[0].tolist(), out
 
-        proto = self._create_controller(configs[0])
-        C = len(configs)
-        if self.config.controller_type in ("pid", "lqr") or len(configs) == 1:
-            ks = [np.ascontiguousarray(self._create_controller(c).effective_gain()) for c in configs] \
-                if C > 1 else [np.ascontiguousarray(proto.effective_gain())]
-            return torch.as_tensor(np.stack(ks), dtype=torch.float64, device=ctx.device), proto
-        lqi = bool(configs[0].get("use_lqi", False))
-        n = 9 if lqi else 6
-        # one numpy conversion per field (a per-candidate loop costs ~100 ms for a 65 536-candidate sweep)
-        q = np.empty((C, n))
-        q[:, 0:3] = np.asarray([c.get("q_pos", _Q_POS_DEFAULT) for c in configs], dtype=np.float64)
-        q[:, 3:6] = np.asarray([c.get("q_vel", _Q_VEL_DEFAULT) for c in configs], dtype=np.float64)
-        if lqi:
-            q[:, 6:9] = np.asarray([c.get("q_int", _Q_INT_DEFAULT) for c in configs], dtype=np.float64)
-        r = np.asarray([c.get("r_controls", _R_DEFAULT) for c in configs], dtype=np.float64).reshape(C, 4)
-        f64 = dict(dtype=torch.float64, device=ctx.device)
-        qd, rd = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
-        A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
-        Q, R = torch.empty((C, n, n), **f64), torch.empty((C, 4, 4), **f64)
-        ctx.build_lqr_systems(n, C, proto.dt, proto.mass, proto.gravity, qd, rd, A, B, Q, R)
-        K = torch.empty((C, 4, n), **f64)
-        iters = torch.zeros(C, dtype=torch.int32, device=ctx.device)
-        info = torch.zeros(C, dtype=torch.int32, device=ctx.device)
-        ctx.dare_batched(n, 4, C, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
-        bad = torch.nonzero(info != 0).reshape(-1).cpu().tolist()
-        if bad:
-            if lqi:
-                raise RuntimeError(f"DARE failed for {len(bad)} LQI candidates (first: {configs[bad[0]]}); "
-                                   "the reference would fall back to the non-integral heuristic LQR")
-            # riccati_lqr.py:747-777: heuristic LQR built from diag(Q), R[0,0], mean(R[1:,1:])
-            for i in bad:
-                Kf = heuristic_lqr_gain(q[i, 0:3], q[i, 3:6], r[i, 0], float(np.mean(r[i, 1:4])))
-                K[i] = torch.as_tensor(Kf, **f64)
-        self.last_dare_info = info
-        self.last_dare_iters = iters
-        return K, proto
+    def evaluate_block(self, block: CandidateBlock, configs: list[dict] | None = None) -> np.ndarray:
+        """Array-native candidate evaluation: float64 [4, C] = score, mean_on_target_ratio, mean_tracking_error,
+        success_rate per candidate (tuning.py:912-926).  No per-candidate Python objects are created."""
+        C = len(block)
+        rows = np.empty((4, C))
+        for i in range(0, C, self.max_batch_candidates):
+            j = min(C, i + self.max_batch_candidates)
+            rows[:, i:j] = self._evaluate_block_launch(block.slice(i, j), None if configs is None else configs[i:j])
+        return rows
 
-    def _evaluate_batch(self, configs: list[dict]) -> tuple[list[float], list[dict]]:
+    def _evaluate_one(self, controller_config: dict) -> tuple[float, float, float, float]:
+        """One candidate through its own controller object (tuning.py:846-928 literally): the constructor solves
+        the DARE and applies the reference's rules — ValueError for malformed weights, heuristic-LQR fallback
+        WITHOUT feedforward and without integral action when the solve fails (riccati_lqr.py:737-777)."""
         import torch
 
         ctx = _lib.get_context()
         ctx.bind_torch_stream()
         cfg = self.config
-        C, eps = len(configs), cfg.evaluation_episodes
         env_config, criteria = self._env_and_criteria()
-        K, proto = self._gains_for(configs, ctx)
-        prm = proto.kernel_params(env_config, criteria)
+        ctrl = self._create_controller(controller_config)
+        prm = ctrl.kernel_params(env_config, criteria)
         f64 = dict(dtype=torch.float64, device=ctx.device)
-        # every candidate sees the same episode seeds seed + ep (tuning.py:875)
-        seeds = torch.arange(eps, dtype=torch.int64, device=ctx.device) + int(cfg.seed)
+        K = torch.as_tensor(np.ascontiguousarray(ctrl.effective_gain()), **f64).reshape(1, 4, ctrl.k_cols())
+        ff = None
+        if prm.feedforward_enabled:
+            ff = torch.as_tensor(np.concatenate([np.asarray(ctrl.ff_velocity_gain, dtype=np.float64).reshape(3),
+                                                 np.asarray(ctrl.ff_acceleration_gain, dtype=np.float64).reshape(3)]),
+                                 **f64).reshape(1, 6)
+        cand = self._sweep_device(ctx, prm, K, ctrl.k_cols(), ff)
+        return tuple(cand.cpu().numpy()[:, 0].tolist())
+
+    def _sweep_device(self, ctx, prm, K, k_cols: int, ff_gains, want_metrics: bool = False):
+        """Reset the evaluation episodes once (every candidate sees the same seeds seed + ep, tuning.py:875) and run
+        all candidates x episodes in one qt_rollout_sweep launch; returns the device [4, C] score rows."""
+        import torch
+
+        cfg = self.config
+        C, eps = int(K.shape[0]), int(cfg.evaluation_episodes)
+        f64 = dict(dtype=torch.float64, device=ctx.device)
+        seeds = torch.empty(eps, dtype=torch.int64, device=ctx.device)
+        ctx.fill_seeds(seeds, int(cfg.seed))
         s0, tp = torch.empty((12, eps), **f64), torch.empty((12, eps), **f64)
         ctx.reset_batched(prm, seeds, s0, tp)
-        state0 = s0.repeat(1, C).contiguous()
-        tparams = tp.repeat(1, C).contiguous()
-        E = C * eps
-        metrics = torch.empty((16, E), **f64)
+        cand = torch.empty((4, C), **f64)
+        metrics = torch.empty((16, C * eps), **f64) if want_metrics else None
+        ctx.rollout_sweep(prm, C, eps, int(cfg.evaluation_horizon), s0, tp, K.contiguous(), k_cols, cand, metrics, ff_gains)
+        self.last_metrics = metrics
+        return cand
+
+    keep_episode_metrics = False   # True: evaluate_* also leave the [16, C*eps] per-episode rows in last_metrics
+
+    def _evaluate_block_launch(self, block: CandidateBlock, configs: list[dict] | None) -> np.ndarray:
+        import torch
+
+        ctx = _lib.get_context()
+        ctx.bind_torch_stream()
+        C = len(block)
+        env_config, criteria = self._env_and_criteria()
+        f64 = dict(dtype=torch.float64, device=ctx.device)
+        proto_cfg = configs[0] if configs is not None else block.config(0)
+        retry: list[int] = []
+        if self.config.controller_type != "riccati_lqr":
+            # PID / heuristic LQR: closed-form gains, one small host computation per candidate
+            proto = self._create_controller(proto_cfg)
+            cfgs = configs if configs is not None else block.configs()
+            ks = np.stack([np.ascontiguousarray(self._create_controller(c).effective_gain()) for c in cfgs])
+            K = torch.as_tensor(ks, **f64)
+        else:
+            lqi = block.use_lqi
+            n = 9 if lqi else 6
+            q = np.empty((C, n))
+            for name, at, default in (("q_pos", 0, _Q_POS_DEFAULT), ("q_vel", 3, _Q_VEL_DEFAULT)) + \
+                    ((("q_int", 6, _Q_INT_DEFAULT),) if lqi else ()):
+                col = block.column(name)
+                q[:, at:at + 3] = default if col is None else col
+            rc = block.column("r_controls")
+            r = np.tile(np.asarray(_R_DEFAULT, dtype=np.float64), (C, 1)) if rc is None else np.ascontiguousarray(rc)
+            # the non-tuned controller parameters (dt, mass, limits, ...) come from a prototype built WITHOUT solving
+            # anything: default weights always solve, the candidates' own weights are solved in the batch below
+            neutral = {k: v for k, v in proto_cfg.items() if k not in ("q_pos", "q_vel", "q_int", "r_controls")}
+            if lqi:
+                neutral["q_int"] = [0.01, 0.01, 0.1]
+            proto = RiccatiLQRController(config=neutral)
+            qd, rd = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
+            A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
+            Q, R = torch.empty((C, n, n), **f64), torch.empty((C, 4, 4), **f64)
+            ctx.build_lqr_systems(n, C, proto.dt, proto.mass, proto.gravity, qd, rd, A, B, Q, R)
+            K = torch.empty((C, 4, n), **f64)
+            iters = torch.zeros(C, dtype=torch.int32, device=ctx.device)
+            info = torch.zeros(C, dtype=torch.int32, device=ctx.device)
+            ctx.dare_batched(n, 4, C, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
+            self.last_dare_info, self.last_dare_iters = info, iters
+            retry = torch.nonzero(info != 0).reshape(-1).cpu().tolist()
+            if retry:
+                K[torch.as_tensor(retry, device=ctx.device)] = 0.0   # placeholder rows, re-evaluated below
+        prm = proto.kernel_params(env_config, criteria)
         ff_gains = None
         if proto.feedforward_enabled:   # per-candidate feedforward gains (tuning.py:700-712)
             ffh = np.zeros((C, 6))
-            for i, c in enumerate(configs):
-                ffh[i, 0:3] = LQRController._ensure_array(c.get("ff_velocity_gain", [0.0, 0.0, 0.0]))
-                ffh[i, 3:6] = LQRController._ensure_array(c.get("ff_acceleration_gain", [0.0, 0.0, 0.0]))
+            for name, at in (("ff_velocity_gain", 0), ("ff_acceleration_gain", 3)):
+                col = block.column(name)
+                if col is not None:
+                    ffh[:, at:at + 3] = col
             ff_gains = torch.as_tensor(ffh, **f64)
-        ctx.rollout(prm, E, int(cfg.evaluation_horizon), 1, state0, tparams, K.contiguous(), proto.k_cols(),
-                    eps, metrics, ff_gains=ff_gains)
-        cand = torch.empty((4, C), **f64)
-        ctx.reduce_scores(metrics, C, eps, cand)
-        host = cand.cpu().numpy()
-        self.last_metrics = metrics
-        scores = host[0].tolist()
-        out = [{"mean_on_target_ratio": a, "mean_tracking_error": b, "success_rate": c_, "episodes_evaluated": eps}
-               for a, b, c_ in zip(host[1].tolist(), host[2].tolist(), host[3].tolist())]
-        return scores, out
+        cand = self._sweep_device(ctx, prm, K, proto.k_cols(), ff_gains, want_metrics=self.keep_episode_metrics)
+        rows = cand.cpu().numpy()
+        # candidates whose DARE failed (or whose weights the validation rejected) go through their own controller
+        # object, one by one, exactly as the reference evaluates them: fallback gain, fallback parameters (no
+        # feedforward, no integral action), ValueError for weights the constructor refuses
+        for i in retry:
+            rows[:, i] = self._evaluate_one(configs[i] if configs is not None else block.config(i))
+        return rows
 
     # -- search loops ----------------------------------------------------------------------------------
     def _record_result(self, config: dict, score: float, metrics: dict) -> None:
@@ -434,21 +586,58 @@ class ControllerTuner:
             self._run_cma_es_search()
             configs = []
         else:
-            remaining = cfg.max_iterations - len(self.results)
-            configs = [self._generate_random_config() for _ in range(max(remaining, 0))]
+            remaining = max(cfg.max_iterations - len(self.results), 0)
+            self._record_block(*self.sweep(remaining))
+            configs = []
         # under torchrun the candidates are split over the ranks (one all_gather of the score rows at the end);
-        # every rank draws the same candidate list from the same seed and ends with the same result
-        from .dist import evaluate_candidates_sharded
+        # every rank ends with the same result
+        from .dist import evaluate_candidates_sharded, is_primary, barrier
 
-        scores, metrics = evaluate_candidates_sharded(self, configs)
-        for c, s, m in zip(configs, scores, metrics):
-            self._record_result(c, s, m)
+        if configs:
+            scores, metrics = evaluate_candidates_sharded(self, configs)
+            for c, s, m in zip(configs, scores, metrics):
+                self._record_result(c, s, m)
         result = TuningResult(
             best_config=self.best_config, best_score=self.best_score, best_metrics=self.best_metrics,
             all_results=self.results, iterations_completed=len(self.results), interrupted=self.interrupted,
             timestamp=datetime.now(timezone.utc).isoformat(), config=cfg.to_dict())
-        self._save_results(result)
+        if is_primary():          # one writer: N ranks would race on the same second-resolution file names
+            self._save_results(result)
+        barrier()
         return result
+
+    def sweep(self, count: int) -> tuple[CandidateBlock, np.ndarray]:
+        """Random search as arrays (BASELINE config 4): draw ``count`` candidates (same generator stream as the
+        reference's loop), evaluate them — over all ranks when launched under torchrun, each rank drawing and
+        scoring its own contiguous shard — and return ``(block, rows)`` with rows float64 [4, count] = score,
+        mean_on_target_ratio, mean_tracking_error, success_rate.  Nothing per candidate is created in Python."""
+        from .dist import gather_candidate_rows, shard_range, world
+
+        rank, size, _ = world()
+        if size == 1:
+            block = self.sample_candidates(count)
+            return block, self.evaluate_block(block)
+        lo, hi = shard_range(count, rank, size)
+        local = self.sample_candidates(count, lo, hi)
+        rows = self.evaluate_block(local) if hi > lo else np.zeros((4, 0))
+        k = local.values.shape[1]
+        packed = np.concatenate([rows, local.values.T.reshape(k, hi - lo)], axis=0)     # [4 + k, C_local]
+        full = gather_candidate_rows(packed, count)
+        block = CandidateBlock(local.spec, np.ascontiguousarray(full[4:].T), local.use_lqi, local.zero_q_int)
+        return block, np.ascontiguousarray(full[:4])
+
+    def _record_block(self, block: CandidateBlock, rows: np.ndarray) -> None:
+        """_record_result for a whole block: the result records are built in one pass, the best candidate is the
+        first of the highest score (strict '>' scan of tuning.py:1084, which also skips NaN scores)."""
+        from .dist import argmax_first
+
+        scores, metrics = self._rows_to_lists(rows)
+        configs = block.configs()
+        self.results.extend({"config": c, "score": s, "metrics": m} for c, s, m in zip(configs, scores, metrics))
+        if len(scores):
+            i = argmax_first(rows[0])
+            if i >= 0 and scores[i] > self.best_score:
+                self.best_score, self.best_config, self.best_metrics = scores[i], configs[i], metrics[i]
 
     # -- CMA-ES (tuning.py:1156-1428): specification, bounds, x0 and sigma0 as in the reference; ask/tell
     # from cmaes.py; one generation = one batched evaluation ------------------------------------------------
@@ -520,7 +709,9 @@ class ControllerTuner:
             solutions = self.cma_es.ask()[: cfg.max_iterations - num_evals]
             repaired = [self.cma_es.repair(x) for x in solutions]
             configs = [self._vector_to_config(x) for x in repaired]
-            scores, metrics = self.evaluate_configs(configs)     # the whole generation in one launch
+            from .dist import evaluate_candidates_sharded
+
+            scores, metrics = evaluate_candidates_sharded(self, configs)   # the whole generation: one launch per rank
             for c, s, m in zip(configs, scores, metrics):
                 self._record_result(c, s, m)
             num_evals += len(solutions)

@@ -54,6 +54,20 @@ def _worker(rank, size, port, total, out_q):
     assert ft.calls == [4 if rank == 0 else 3]
     assert sc == [0.5 * i for i in range(7)] and [m["mean_tracking_error"] for m in me] == [1.0 + i for i in range(7)]
     assert all(m["episodes_evaluated"] == 3 and m["success_rate"] == 1.0 for m in me)
+    # a state-carrying controller under Evaluator semantics (LQI, eval.py:198-213): rank 0 owns the whole chain, the
+    # other rank contributes an EMPTY shard (n = 0) and receives the summary and the controller's final state
+    lo2, hi2, chain = qd.evaluation_shard_plan(total, rank, size, carries_over=True)
+    assert (lo2, hi2, chain) == ((0, total, total) if rank == 0 else (0, 0, 1))
+    sums2 = torch.from_numpy(_shard_sums(ratios, errs)) if rank == 0 else torch.zeros(16, dtype=torch.float64)
+    state = torch.tensor([1.5, -2.5, 3.5, 7.0], dtype=torch.float64) if rank == 0 else torch.zeros(4, dtype=torch.float64)
+    summary2, merged2 = qd.reduce_summary_across_ranks(sums2, lo2, SuccessCriteria(), extra=state)
+    assert summary2.total_episodes == total and abs(summary2.mean_on_target_ratio - ratios.mean()) < 1e-13
+    assert summary2.best_episode_idx == int(np.argmax(ratios))
+    assert merged2["extra"][0].tolist() == [1.5, -2.5, 3.5, 7.0]
+    # candidate rows with parameter rows riding along (ControllerTuner.sweep): unequal shards, numpy in / out
+    rows = np.arange(6 * C, dtype=np.float64).reshape(6, C)
+    assert qd.gather_candidate_rows(rows[:, clo:chi], C).tolist() == rows.tolist()
+    assert qd.evaluate_candidates_sharded(ft, []) == ([], [])    # nothing to score: returns before any collective
     out_q.put((rank, summary.mean_on_target_ratio, summary.std_on_target_ratio, summary.best_episode_idx,
                summary.worst_episode_idx, summary.total_episodes, full.numpy().tolist()))
     torch.distributed.destroy_process_group()

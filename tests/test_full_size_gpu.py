@@ -105,10 +105,19 @@ def test_full_size_config4_autotune_sweep_65536_candidates(gpu_ctx, tmp_path):
     tuner = ControllerTuner(tc)
     half = [tuner._generate_random_config() for _ in range(C // 2)]
     configs = half + half[::-1]                       # every candidate appears twice, mirrored
+    fused_scores, fused_metrics = tuner.evaluate_configs(configs)     # production path: reduction fused into the rollout
+    assert tuner.last_metrics is None                                 # ... and no per-episode rows written
+    tuner.keep_episode_metrics = True                                 # same launch, rows written as well
     scores, metrics = tuner.evaluate_configs(configs)
+    assert scores == fused_scores and metrics == fused_metrics       # bit-identical either way
     s = np.array(scores)
     assert len(scores) == C and np.isfinite(s).all()
     np.testing.assert_array_equal(s[:C // 2], s[C // 2:][::-1])
+    # the array-native sweep (ControllerTuner.sweep) draws the same candidates and scores them identically
+    tuner2 = ControllerTuner(tc)
+    block, rows = tuner2.sweep(C // 2)
+    assert block.configs()[:3] == half[:3] and block.config(C // 2 - 1) == half[-1]
+    np.testing.assert_array_equal(rows[0], s[:C // 2])
     assert bool((tuner.last_dare_info == 0).all())
     it = tuner.last_dare_iters.cpu().numpy()
     assert it.min() >= 8 and it.max() <= 24           # doubling converges quadratically on these ranges

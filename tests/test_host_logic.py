@@ -11,7 +11,7 @@ from lqr_quadcopter_test_b200.controller import (build_augmented_lqi_system, bui
 from lqr_quadcopter_test_b200.dist import shard_range
 from lqr_quadcopter_test_b200.metrics import (EpisodeMetricsView, SuccessCriteria, episode_metrics_from_vector,
                                               merge_summary_sums, summary_from_sums)
-from lqr_quadcopter_test_b200.tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
+from lqr_quadcopter_test_b200.tuning import CandidateBlock, ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
 
 
 def test_env_config_round_trip_and_legacy_keys():
@@ -104,6 +104,75 @@ def test_random_candidates_consume_the_rng_like_the_reference(golden, lqi, tmp_p
     np.testing.assert_array_equal(q, g[key + "_q"])
     np.testing.assert_array_equal(r, g[key + "_r"])
     assert all(c.get("use_lqi", False) == lqi for c in cfgs)
+
+
+def _full_space():
+    return GainSearchSpace(kp_pos_range=([0.001, 0.001, 1.0], [0.1, 0.1, 8.0]), kd_pos_range=([0.01] * 3, [0.2, 0.2, 4.0]),
+                           ff_velocity_gain_range=([0.0] * 3, [0.3] * 3), q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]),
+                           r_thrust_range=(0.5, 2.0), r_rate_range=(0.1, 1.0), r_controls_range=([0.5] * 4, [2.0] * 4),
+                           q_int_range=([1e-6, 1e-6, 1e-4], [1e-5, 1e-5, 1e-2]))
+
+
+@pytest.mark.parametrize("space", ["riccati", "riccati_lqi", "everything", "use_lqi_flag"])
+def test_vectorised_sampling_is_the_scalar_draw_sequence(golden, space, tmp_path):
+    """sample_candidates (one rng.uniform block) against _generate_random_config called in a loop (the reference's
+    scalar draws, tuning.py:683-735; itself pinned to the reference's fixture above): identical dictionaries,
+    identical generator state afterwards, and a rank's shard [lo, hi) equals the same rows of the full draw."""
+    sp = {"riccati": _riccati_space(False), "riccati_lqi": _riccati_space(True), "everything": _full_space(),
+          "use_lqi_flag": GainSearchSpace(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), use_lqi=True)}[space]
+    mk = lambda: ControllerTuner(TuningConfig(controller_type="riccati_lqr", search_space=sp, seed=42, output_dir=str(tmp_path)))
+    C = 257
+    a, b = mk(), mk()
+    scalar = [a._generate_random_config() for _ in range(C)]
+    block = b.sample_candidates(C)
+    assert block.configs() == scalar
+    assert a.rng.random() == b.rng.random()                     # both generators ended in the same state
+    if space == "riccati":
+        g = golden["tuning"]
+        np.testing.assert_array_equal(np.concatenate([block.column("q_pos"), block.column("q_vel")], axis=1)[:5], g["riccati_stationary_q"])
+        np.testing.assert_array_equal(block.column("r_controls")[:5], g["riccati_stationary_r"])
+    for lo, hi in ((0, 100), (100, 101), (101, 257), (257, 257)):
+        c = mk()
+        part = c.sample_candidates(C, lo, hi)
+        np.testing.assert_array_equal(part.values, block.values[lo:hi])
+        assert c.rng.random() == mk_state_after(sp, tmp_path, C)
+    # dictionaries -> block -> dictionaries is the identity
+    again = CandidateBlock.from_configs(scalar)
+    assert again is not None and again.configs() == scalar and again.use_lqi == block.use_lqi
+    assert CandidateBlock.from_configs(scalar[:3] + [{"kd_pos": [0.1, 0.1, 1.0], "mass": 2.0}]) is None   # other keys: not one block
+
+
+def mk_state_after(sp, tmp_path, C):
+    t = ControllerTuner(TuningConfig(controller_type="riccati_lqr", search_space=sp, seed=42, output_dir=str(tmp_path)))
+    t.sample_candidates(C)
+    return t.rng.random()
+
+
+def test_argmax_first_follows_the_strict_scan():
+    """tuning.py:1084: `if score > best_score` while scanning — first of equal scores, NaN never wins."""
+    from lqr_quadcopter_test_b200.dist import argmax_first
+
+    def scan(scores):
+        best, idx = float("-inf"), -1
+        for i, s in enumerate(scores):
+            if s > best:
+                best, idx = s, i
+        return idx
+
+    for scores in ([0.1, 0.5, 0.5, 0.2], [float("nan"), 0.3, 0.7], [0.3, float("nan"), 0.3], [float("nan")] * 3,
+                   [float("-inf"), float("-inf")], [1.0]):
+        got = argmax_first(np.array(scores))
+        want = scan(scores)
+        assert got == want or (want == -1 and (got == -1 or scores[got] == float("-inf"))), (scores, got, want)
+
+
+def test_evaluation_shard_plan():
+    from lqr_quadcopter_test_b200.dist import evaluation_shard_plan
+
+    assert [evaluation_shard_plan(10, r, 4, False) for r in range(4)] == [(0, 3, 1), (3, 6, 1), (6, 8, 1), (8, 10, 1)]
+    # a controller that carries state across episodes (LQI under Evaluator semantics, eval.py:198-213): one chain on rank 0
+    assert [evaluation_shard_plan(10, r, 4, True) for r in range(4)] == [(0, 10, 10), (0, 0, 1), (0, 0, 1), (0, 0, 1)]
+    assert evaluation_shard_plan(1, 0, 2, True) == (0, 1, 2)
 
 
 def test_grid_candidates_match_the_reference(golden, tmp_path):
