@@ -11,18 +11,36 @@
 // ordered QZ decomposition of the 2n x 2n symplectic pencil instead; both compute the same
 // stabilising solution, agreement is checked to 1e-9 relative on K (tests/test_dare_gpu.py).
 //
-// Mapping: these are tiny, non-GEMM solves — no tensor cores.  A "team" of N lanes of one
-// warp owns one system, lane i holding row i of every matrix in registers; 32/N systems share a
-// warp.  Products need the other lanes' rows, which are staged in shared memory (padded row
-// stride, 16-byte LDS broadcasts); W is inverted by Gauss-Jordan elimination with partial
-// pivoting carried out across the team (pivot search and pivot-row broadcast through shared
-// memory, __syncwarp between phases).  n and m are zero-padded to the next instantiated N,
-// which leaves the solution of the original system unchanged (block-diagonal embedding).
+// Mapping: these are tiny, non-GEMM solves — no tensor cores.  A "team" of N / R lanes of one warp owns one system,
+// each lane holding R consecutive rows of every matrix in registers; 32 / (N / R) systems share a warp (N = 6, R = 2:
+// ten systems per warp on 30 lanes).  A product needs the other lanes' rows, which are staged in shared memory and
+// read with 16-byte broadcast loads: one load feeds 2 R fused multiply-adds (4 R where two products share an
+// operand), so with R = 2 the kernel issues half the shared-memory wavefronts per flop of the one-row-per-lane
+// layout of round 1, whose limiter they were (ncu r01_e: LSU pipe busier than the FP64 pipe, 59 % of the stall
+// samples on the shared-memory scoreboard / queue).  W is inverted by Gauss-Jordan elimination with partial pivoting
+// across the team: pivot search with 32-bit shuffle keys, pivot rows broadcast through shared memory, one
+// elimination pass per column over all R rows of a lane (the pivot row itself takes a zero multiplier, so the pass
+// is branch free).  n and m are zero-padded to the next instantiated N, which leaves the solution of the original
+// system unchanged (block-diagonal embedding).
 #include "qt_common.cuh"
 
 namespace qt {
 
-constexpr int kDareWarps = 4;
+// A/B switches for the larger sizes (defaults = the measured winners)
+#ifndef QT_DARE_N9
+#define QT_DARE_N9 9     // n = 7..9 (LQI): 3 lanes x 3 rows, 10 systems per warp
+#define QT_DARE_R9 3
+#endif
+#ifndef QT_DARE_R6
+#define QT_DARE_R6 3     // n = 5, 6: 2 lanes x 3 rows, 16 systems per warp
+#endif
+#ifndef QT_DARE_R12
+#define QT_DARE_R12 2    // 6 lanes x 2 rows, 5 systems per warp
+#endif
+#ifndef QT_DARE_R16
+#define QT_DARE_R16 1    // 16 lanes x 1 row, 2 systems per warp (2 rows per lane spill)
+#endif
+
 constexpr int kDareMaxIter = 64;
 constexpr double kDareTol = 1e-14;  // relative Frobenius change of H
 
@@ -35,60 +53,29 @@ struct DareArgs {
     int32_t *iters, *info;
 };
 
-template <int N>
+template <int N, int R>
 struct Lay {
+    static_assert(N % R == 0, "N must be a multiple of the rows per lane");
+    static constexpr int TEAM = N / R;             // lanes per system
     static constexpr int LD = (N + 1) & ~1;        // even row stride: rows stay 16-byte aligned
     static constexpr int MAT = N * LD;
-    static constexpr int RAW = 6 * MAT + 4 * LD;   // sA sG sH sX sY sS | pivot row (3 LD) | column (LD)
-    // Teams of one warp issue the same 16-byte broadcast load at the same offset inside their own
-    // block; padding the block to 2 (mod 16) doubles = 4 (mod 32) banks puts up to 8 teams on
-    // disjoint bank groups (the unpadded N = 6 layout was a 5-way conflict: ncu, profiles/r01_a).
-    static constexpr int TEAM = RAW + ((2 - RAW % 16) + 16) % 16;
-    static constexpr int TEAMS = 32 / N;           // systems per warp
-    static constexpr int SLOTS = TEAMS + ((32 % N) ? 1 : 0);  // + a ghost team for leftover lanes
+    static constexpr int RAW = 4 * MAT + 4 * LD;   // sA sH sX sY | pivot rows (3 LD) + 1/pivot (LD)
+    // Teams of one warp issue the same 16-byte broadcast load at the same offset inside their own block; padding
+    // the block to 2 (mod 16) doubles = 4 (mod 32) banks puts neighbouring teams on disjoint bank groups (the
+    // unpadded N = 6 layout of the first version was a 5-way conflict: ncu, profiles/r01_a).
+    static constexpr int BLOCK = RAW + ((2 - RAW % 16) + 16) % 16;
+    static constexpr int TEAMS = 32 / TEAM;        // systems per warp
+    static constexpr int SLOTS = TEAMS + ((32 % TEAM) ? 1 : 0);  // + a ghost team for leftover lanes
 };
 
-// c[j] (+)= sum_k x[k] * Y[k][j],  Y row-major in shared memory
-template <int N, bool ACCUM>
-__device__ __forceinline__ void row_times(const double (&x)[N], const double *__restrict__ Y,
-                                          double (&c)[N]) {
-    constexpr int LD = Lay<N>::LD;
-    if (!ACCUM) {
-#pragma unroll
-        for (int j = 0; j < N; j++) c[j] = 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-#pragma unroll
-        for (int j = 0; j < N; j += 2) {
-            const double2 y = *reinterpret_cast<const double2 *>(Y + k * LD + j);
-            c[j] = fma(x[k], y.x, c[j]);
-            if (j + 1 < N) c[j + 1] = fma(x[k], y.y, c[j + 1]);
-        }
-    }
-}
-
-// c[j] += sum_k x[k] * Y[j][k]   (product with the transpose of Y)
+// NOTE: none of the shared-memory pointers below is __restrict__-qualified.  The team's lanes communicate through
+// these buffers (a row stored by one lane is loaded by the others after a __syncwarp), and with restrict the
+// compiler may keep or forward values across that barrier: the first version of this kernel with restrict on the
+// helpers returned garbage for every system on sm_100a (nvcc 12.9) while a lane-by-lane CPU emulation of the same
+// source was exact.
 template <int N>
-__device__ __forceinline__ void row_times_T(const double (&x)[N], const double *__restrict__ Y,
-                                            double (&c)[N]) {
-    constexpr int LD = Lay<N>::LD;
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-        double acc = c[j];
-#pragma unroll
-        for (int k = 0; k < N; k += 2) {
-            const double2 y = *reinterpret_cast<const double2 *>(Y + j * LD + k);
-            acc = fma(x[k], y.x, acc);
-            if (k + 1 < N) acc = fma(x[k + 1], y.y, acc);
-        }
-        c[j] = acc;
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void store_row(double *__restrict__ M, int row, const double (&x)[N]) {
-    constexpr int LD = Lay<N>::LD;
+__device__ __forceinline__ void store_row(double *M, int row, const double (&x)[N]) {
+    constexpr int LD = (N + 1) & ~1;
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
         double2 v;
@@ -98,270 +85,474 @@ __device__ __forceinline__ void store_row(double *__restrict__ M, int row, const
     }
 }
 
-// c1[j] = sum_k x1[k] * Y[k][j] and c2[j] = sum_k x2[k] * Y[k][j]: two products sharing the loads of Y
 template <int N>
-__device__ __forceinline__ void row_times2(const double (&x1)[N], const double (&x2)[N],
-                                           const double *__restrict__ Y, double (&c1)[N], double (&c2)[N]) {
-    constexpr int LD = Lay<N>::LD;
+__device__ __forceinline__ void load_row(const double *M, int row, double (&x)[N]) {
+    constexpr int LD = (N + 1) & ~1;
 #pragma unroll
-    for (int j = 0; j < N; j++) c1[j] = c2[j] = 0.0;
+    for (int j = 0; j < N; j += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(M + row * LD + j);
+        x[j] = v.x;
+        if (j + 1 < N) x[j + 1] = v.y;
+    }
+}
+
+// c[r][j] (+)= sum_k x[r][k] * Y[k][j] for the R rows of this lane,  Y row-major in shared memory
+template <int N, int R, bool ACCUM>
+__device__ __forceinline__ void rows_times(const double (&x)[R][N], const double *Y, double (&c)[R][N]) {
+    constexpr int LD = (N + 1) & ~1;
+    if (!ACCUM) {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++) c[r][j] = 0.0;
+    }
 #pragma unroll
     for (int k = 0; k < N; k++) {
 #pragma unroll
         for (int j = 0; j < N; j += 2) {
             const double2 y = *reinterpret_cast<const double2 *>(Y + k * LD + j);
-            c1[j] = fma(x1[k], y.x, c1[j]);
-            c2[j] = fma(x2[k], y.x, c2[j]);
-            if (j + 1 < N) {
-                c1[j + 1] = fma(x1[k], y.y, c1[j + 1]);
-                c2[j + 1] = fma(x2[k], y.y, c2[j + 1]);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                c[r][j] = fma(x[r][k], y.x, c[r][j]);
+                if (j + 1 < N) c[r][j + 1] = fma(x[r][k], y.y, c[r][j + 1]);
             }
         }
     }
 }
 
-// Gauss-Jordan with partial pivoting, one matrix row per lane.  On exit the lane that served
-// as pivot for column c holds row c of W^-1 [R1 | R2] in (r1 | r2); it writes them to
-// X[c][:] / Y[c][:].  Returns false if a pivot was zero / not finite.
+// c1 = x1 Y and c2 = x2 Y: two products sharing the loads of Y (4 R multiply-adds per 16-byte load)
+template <int N, int R>
+__device__ __forceinline__ void rows_times2(const double (&x1)[R][N], const double (&x2)[R][N],
+                                            const double *Y, double (&c1)[R][N], double (&c2)[R][N]) {
+    constexpr int LD = (N + 1) & ~1;
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int j = 0; j < N; j++) c1[r][j] = c2[r][j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            const double2 y = *reinterpret_cast<const double2 *>(Y + k * LD + j);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                c1[r][j] = fma(x1[r][k], y.x, c1[r][j]);
+                c2[r][j] = fma(x2[r][k], y.x, c2[r][j]);
+                if (j + 1 < N) {
+                    c1[r][j + 1] = fma(x1[r][k], y.y, c1[r][j + 1]);
+                    c2[r][j + 1] = fma(x2[r][k], y.y, c2[r][j + 1]);
+                }
+            }
+        }
+    }
+}
+
+// c[r][j] += sum_k x[r][k] * Y[j][k]   (product with the transpose of Y)
+template <int N, int R>
+__device__ __forceinline__ void rows_times_T(const double (&x)[R][N], const double *Y, double (&c)[R][N]) {
+    constexpr int LD = (N + 1) & ~1;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = c[r][j];
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            const double2 y = *reinterpret_cast<const double2 *>(Y + j * LD + k);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                acc[r] = fma(x[r][k], y.x, acc[r]);
+                if (k + 1 < N) acc[r] = fma(x[r][k + 1], y.y, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) c[r][j] = acc[r];
+    }
+}
+
+// Gauss-Jordan with partial pivoting, R matrix rows per lane.  On exit the (lane, slot) that served as pivot for
+// column c holds row c of W^-1 [R1 | R2] in (r1 | r2) and has written it to X[c][:] / Y[c][:].  Returns false if a
+// pivot was zero / not finite.
 //
-// Per column: (1) pivot search without shared memory — every lane publishes a 32-bit key (the
-// high word of |w[c]| with the lane index in its low 5 bits, 0 for rows already used) and reads
-// its team mates' keys with shuffles; the top 27 bits of the magnitude are plenty for partial
-// pivoting; (2) the pivot lane writes its row and 1/pivot to shared memory; (3) the other lanes
-// eliminate.  Rows are not normalised until the end.  The multiplier is w[c] * (1/pivot): the
-// matrices of the reference's designs are sparse, and CUDA's double division takes its slow path
-// for a zero numerator, which made one third of the first version's instructions.
-template <int N, bool TWO>
-__device__ __forceinline__ bool gauss_jordan(double (&w)[N], double (&r1)[N], double (&r2)[N],
-                                             double *__restrict__ sRow, double *__restrict__ X,
-                                             double *__restrict__ Y, int li, int team_base) {
-    constexpr int LD = Lay<N>::LD;
-    bool used = false, ok = true;
-    int my_col = 0;
-    double my_inv = 1.0;
+// Per column: (1) pivot search without shared memory — every lane publishes one 32-bit key (the top 26 bits of the
+// high word of |w[c]| of its best unused row, that row's index in the low 6 bits, inverted so the lowest row wins
+// ties) and reads its team mates' keys with shuffles; (2) the owner writes the pivot row and 1/pivot to shared
+// memory; (3) every lane eliminates in all of its R rows — the pivot row itself with a zero multiplier, which leaves
+// it unchanged without a branch.  Rows are not normalised until the end.  The multiplier is w[c] * (1/pivot): the
+// matrices of the reference's designs are sparse, and CUDA's double division takes its slow path for a zero
+// numerator, which made one third of the first version's instructions.
+template <int N, int R, bool TWO>
+__device__ __forceinline__ bool gauss_jordan(double (&w)[R][N], double (&r1)[R][N], double (&r2)[R][N],
+                                             double *sRow, double *X,
+                                             double *Y, int li, int team_base) {
+    constexpr int LD = (N + 1) & ~1, TEAM = N / R;
+    bool ok = true;
+    bool used[R];
+    int my_col[R];
+    double my_inv[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        used[r] = false;
+        my_col[r] = 0;
+        my_inv[r] = 1.0;
+    }
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        const unsigned hi = (unsigned)__double2hiint(w[c]) & 0x7fffffffu;
-        const unsigned key = used ? 0u : ((hi & 0xffffffe0u) | (unsigned)(31 - li));
+        unsigned key = 0u;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const unsigned hi = (unsigned)__double2hiint(w[r][c]) & 0x7fffffffu;
+            const unsigned k = used[r] ? 0u : ((hi & 0xffffffc0u) | (unsigned)(63 - (li * R + r)));
+            key = max(key, k);
+        }
         unsigned best = 0u;
 #pragma unroll
-        for (int k = 0; k < N; k++) best = max(best, __shfl_sync(0xffffffffu, key, team_base + k));
-        const int p = 31 - (int)(best & 31u);
-        if ((best >> 5) == 0u || best >= 0x7ff00000u) ok = false;  // zero / NaN / inf pivot
-        if (li == p) {
-            used = true;
-            my_col = c;
-            my_inv = 1.0 / w[c];
-            // only columns > c of W are still needed by the other rows
+        for (int k = 0; k < TEAM; k++) best = max(best, __shfl_sync(0xffffffffu, key, team_base + k));
+#ifdef QT_DARE_EXTRA_SYNC
+        __syncwarp();
+#endif
+        const int prow = 63 - (int)(best & 63u);
+        if ((best >> 6) == 0u || best >= 0x7ff00000u) ok = false;  // zero / NaN / inf pivot
+        const int pl = prow / R, ps = prow % R;
+        if (li == pl) {
 #pragma unroll
-            for (int j = c & ~1; j < N; j += 2) {
-                double2 v;
-                v.x = w[j];
-                v.y = (j + 1 < N) ? w[j + 1] : 0.0;
-                *reinterpret_cast<double2 *>(sRow + j) = v;
+            for (int r = 0; r < R; r++) {
+                if (ps == r) {
+                    used[r] = true;
+                    my_col[r] = c;
+                    my_inv[r] = 1.0 / w[r][c];
+                    // only columns > c of W are still needed by the other rows
+#pragma unroll
+                    for (int j = c & ~1; j < N; j += 2) {
+                        double2 v;
+                        v.x = w[r][j];
+                        v.y = (j + 1 < N) ? w[r][j + 1] : 0.0;
+                        *reinterpret_cast<double2 *>(sRow + j) = v;
+                    }
+                    store_row<N>(sRow + LD, 0, r1[r]);
+                    if (TWO) store_row<N>(sRow + 2 * LD, 0, r2[r]);
+                    sRow[3 * LD] = my_inv[r];
+                }
             }
-            store_row<N>(sRow + LD, 0, r1);
-            if (TWO) store_row<N>(sRow + 2 * LD, 0, r2);
-            sRow[3 * LD] = my_inv;
         }
         __syncwarp();
-        if (li != p) {
-            const double f = w[c] * sRow[3 * LD];
+        {
+            const double inv = sRow[3 * LD];
+            double f[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const bool is_pivot = (li == pl) & (ps == r);
+                f[r] = is_pivot ? 0.0 : w[r][c] * inv;
+                w[r][c] = is_pivot ? w[r][c] : 0.0;
+            }
 #pragma unroll
             for (int j = (c + 1) & ~1; j < N; j += 2) {
                 const double2 y = *reinterpret_cast<const double2 *>(sRow + j);
-                if (j > c) w[j] = fma(-f, y.x, w[j]);
-                if (j + 1 < N) w[j + 1] = fma(-f, y.y, w[j + 1]);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (j > c) w[r][j] = fma(-f[r], y.x, w[r][j]);
+                    if (j + 1 < N) w[r][j + 1] = fma(-f[r], y.y, w[r][j + 1]);
+                }
             }
-            w[c] = 0.0;
 #pragma unroll
             for (int j = 0; j < N; j += 2) {
                 const double2 y = *reinterpret_cast<const double2 *>(sRow + LD + j);
-                r1[j] = fma(-f, y.x, r1[j]);
-                if (j + 1 < N) r1[j + 1] = fma(-f, y.y, r1[j + 1]);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    r1[r][j] = fma(-f[r], y.x, r1[r][j]);
+                    if (j + 1 < N) r1[r][j + 1] = fma(-f[r], y.y, r1[r][j + 1]);
+                }
             }
             if (TWO) {
 #pragma unroll
                 for (int j = 0; j < N; j += 2) {
                     const double2 y = *reinterpret_cast<const double2 *>(sRow + 2 * LD + j);
-                    r2[j] = fma(-f, y.x, r2[j]);
-                    if (j + 1 < N) r2[j + 1] = fma(-f, y.y, r2[j + 1]);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        r2[r][j] = fma(-f[r], y.x, r2[r][j]);
+                        if (j + 1 < N) r2[r][j + 1] = fma(-f[r], y.y, r2[r][j + 1]);
+                    }
                 }
             }
         }
         __syncwarp();
     }
 #pragma unroll
-    for (int j = 0; j < N; j++) {
-        r1[j] *= my_inv;
-        if (TWO) r2[j] *= my_inv;
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            r1[r][j] *= my_inv[r];
+            if (TWO) r2[r][j] *= my_inv[r];
+        }
+        store_row<N>(X, my_col[r], r1[r]);
+        if (TWO) store_row<N>(Y, my_col[r], r2[r]);
     }
-    store_row<N>(X, my_col, r1);
-    if (TWO) store_row<N>(Y, my_col, r2);
     __syncwarp();
     return ok;
 }
 
-// (launch bounds: resident blocks per SM the register allocator must allow — the kernel is
-// latency-bound, so occupancy matters: 4 blocks for N <= 6, 3 for N = 9)
-template <int N>
-__global__ void __launch_bounds__(kDareWarps * 32, (N <= 6 ? 4 : (N <= 9 ? 3 : 1)))
+// sum of v over the lanes of the team, the same order in every lane (so all lanes hold identical bits)
+template <int TEAM>
+__device__ __forceinline__ double team_sum(double v, int team_base) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < TEAM; k++) s += __shfl_sync(0xffffffffu, v, team_base + k);
+    return s;
+}
+
+template <int N, int R>
+struct DareCfg {
+    static constexpr int RN = R * N;  // doubles per matrix held by one lane; ~4 RN doubles are live at the widest point
+    // warps per block and resident blocks per SM the register allocator must allow (shared memory per team is
+    // 4 N^2 + 4 N doubles, which is what bounds the residency of the larger sizes)
+    // (measured, profiles/r02_e_dare_ab.txt: n = 6 as 2 lanes x 3 rows runs 1.45e8 solves/s with 3-warp blocks and
+    // 1.76e8 with 4-warp blocks at 2 blocks per SM — the register file is allocated per 4 warps)
+    static constexpr int WARPS = RN <= 20 ? 4 : 3;
+    static constexpr int MIN_BLOCKS = RN <= 12 ? 3 : 2;
+};
+#if defined(QT_DARE_W6) && defined(QT_DARE_B6)   // A/B: block shape of the n = 6 kernel
+template <>
+struct DareCfg<6, QT_DARE_R6> {
+    static constexpr int RN = 6 * QT_DARE_R6, WARPS = QT_DARE_W6, MIN_BLOCKS = QT_DARE_B6;
+};
+#endif
+#if defined(QT_DARE_W9) && defined(QT_DARE_B9)   // A/B: block shape of the n = 9 kernel
+template <>
+struct DareCfg<QT_DARE_N9, QT_DARE_R9> {
+    static constexpr int RN = QT_DARE_N9 * QT_DARE_R9, WARPS = QT_DARE_W9, MIN_BLOCKS = QT_DARE_B9;
+};
+#endif
+
+template <int N, int R>
+__device__ __forceinline__ void load_rows(const double *M, int row0, double (&x)[R][N]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) load_row<N>(M, row0 + r, x[r]);
+}
+
+template <int N, int R>
+__device__ __forceinline__ void store_rows(double *M, int row0, const double (&x)[R][N]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) store_row<N>(M, row0 + r, x[r]);
+}
+
+template <int N, int R>
+__global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_BLOCKS)
     dare_kernel(const __grid_constant__ DareArgs D) {
     extern __shared__ __align__(16) double smem[];
-    using L = Lay<N>;
-    constexpr int LD = L::LD;
+    using L = Lay<N, R>;
+    constexpr int LD = L::LD, TEAM = L::TEAM, WARPS = DareCfg<N, R>::WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int team = lane / N, li = lane % N, team_base = lane - li;
-    const int64_t sys = ((int64_t)blockIdx.x * kDareWarps + warp) * L::TEAMS + team;
+    const int team = lane / TEAM, li = lane % TEAM, team_base = lane - li;
+    const int row0 = li * R;  // first matrix row held by this lane
+    const int64_t sys = ((int64_t)blockIdx.x * WARPS + warp) * L::TEAMS + team;
     const int n = D.n, m = D.m;
     bool ghost = (team >= L::TEAMS) || (sys >= D.batch);
     if (!ghost && D.info[sys] == 3) ghost = true;  // rejected by the validation kernel
 
-    double *tb = smem + (size_t)(warp * L::SLOTS + team) * L::TEAM;
-    double *sA = tb, *sG = tb + L::MAT, *sH = tb + 2 * L::MAT, *sX = tb + 3 * L::MAT,
-           *sY = tb + 4 * L::MAT, *sS = tb + 5 * L::MAT, *sRow = tb + 6 * L::MAT;  // sRow: 3 LD + 1/pivot
+    // Shared memory of one team: four N x N matrices and the pivot-row buffer.  pA holds A_k, pY receives
+    // Y = W^-1 G_k and then A_{k+1} (the two pointers are exchanged at the end of a doubling), sH holds H_k,
+    // sX receives X = W^-1 A_k and then H_k X.  G_k is only ever needed row-wise by its owner: registers.
+    double *tb = smem + (size_t)(warp * L::SLOTS + team) * L::BLOCK;
+    double *pA = tb, *sH = tb + L::MAT, *sX = tb + 2 * L::MAT, *pY = tb + 3 * L::MAT, *sRow = tb + 4 * L::MAT;
 
     const double *Ap = ghost ? nullptr : D.A + sys * D.sA;
     const double *Bp = ghost ? nullptr : D.B + sys * D.sB;
     const double *Qp = ghost ? nullptr : D.Q + sys * D.sQ;
     const double *Rp = ghost ? nullptr : D.R + sys * D.sR;
 
-    double a[N], g[N], h[N], brow[N];
+    auto load_global_rows = [&](const double *M, int rows, int cols, double (&x)[R][N]) {  // zero-padded rows of M
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                x[r][j] = (!ghost && row0 + r < rows && j < cols) ? M[(row0 + r) * cols + j] : 0.0;
+    };
+    auto load_R_pad = [&](double (&w)[R][N]) {  // R_pad = blockdiag(R, I)
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                w[r][j] = (!ghost && row0 + r < m && j < m) ? Rp[(row0 + r) * m + j] : (row0 + r == j ? 1.0 : 0.0);
+    };
+
+    double g[R][N];
     bool ok = true;
     {
-        // R_pad = blockdiag(R, I), rows of B'_pad as right-hand side:  Z = R^-1 B'
-        double w[N], r1[N], r2[N];
+        // G0 = B R^-1 B':  Z = R_pad^-1 B'_pad (rows of B' as right-hand side), then G0 = B Z
+        double w[R][N], r1[R][N], r2[R][N];
+        load_R_pad(w);
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            const bool in_a = !ghost && li < n && j < n;
-            a[j] = in_a ? Ap[li * n + j] : 0.0;
-            h[j] = in_a ? Qp[li * n + j] : 0.0;
-            brow[j] = (!ghost && li < n && j < m) ? Bp[li * m + j] : 0.0;
-            w[j] = (!ghost && li < m && j < m) ? Rp[li * m + j] : (li == j ? 1.0 : 0.0);
-            r1[j] = (!ghost && li < m && j < n) ? Bp[j * m + li] : 0.0;
-            r2[j] = 0.0;
-        }
-        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sX, sY, li, team_base);
-        row_times<N, false>(brow, sX, g);  // G0 = B Z
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                r1[r][j] = (!ghost && row0 + r < m && j < n) ? Bp[j * m + row0 + r] : 0.0;
+                r2[r][j] = 0.0;
+            }
+        ok &= gauss_jordan<N, R, false>(w, r1, r2, sRow, sX, pY, li, team_base);
+        double brow[R][N];
+        load_global_rows(Bp, n, m, brow);
+        rows_times<N, R, false>(brow, sX, g);
+        double a[R][N], h[R][N];
+        load_global_rows(Ap, n, n, a);
+        load_global_rows(Qp, n, n, h);
+        __syncwarp();  // every lane has read Z
+        store_rows<N, R>(pA, row0, a);
+        store_rows<N, R>(sH, row0, h);
     }
 
     bool conv = false;
     int iters = 0;
     for (int it = 0; it < kDareMaxIter; it++) {
         if (__all_sync(0xffffffffu, conv || ghost)) break;
-        store_row<N>(sA, li, a);
-        store_row<N>(sG, li, g);
-        store_row<N>(sH, li, h);
-        __syncwarp();
-        double an[N], gn[N], hn[N];
+        __syncwarp();  // the rows of A_k / H_k stored by the team are visible
         {
-            double w[N], r1[N], r2[N];
-            row_times<N, false>(g, sH, w);  // G H
+            double w[R][N], r1[R][N], r2[R][N];
+            rows_times<N, R, false>(g, sH, w);  // G H
+            load_rows<N, R>(pA, row0, r1);
 #pragma unroll
-            for (int j = 0; j < N; j++) {
-                w[j] += (j == li) ? 1.0 : 0.0;  // W = I + G H
-                r1[j] = a[j];
-                r2[j] = g[j];
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    w[r][j] += (j == row0 + r) ? 1.0 : 0.0;  // W = I + G H
+                    r2[r][j] = g[r][j];
+                }
+            const bool gj_ok = gauss_jordan<N, R, true>(w, r1, r2, sRow, sX, pY, li, team_base);  // X -> sX, Y -> pY
+            ok &= conv || gj_ok;
+        }
+        {
+            double a[R][N];
+            load_rows<N, R>(pA, row0, a);
+            {
+                double t[R][N];
+                rows_times<N, R, false>(a, pY, t);  // A Y
+                rows_times_T<N, R>(t, pA, g);       // G_{k+1} = G + (A Y) A'
             }
-            ok &= gauss_jordan<N, true>(w, r1, r2, sRow, sX, sY, li, team_base);  // X = W^-1 A, Y = W^-1 G
+            double an[R][N];
+            rows_times<N, R, false>(a, sX, an);     // A_{k+1} = A X
+            __syncwarp();                           // every lane has read Y: pY now receives A_{k+1}
+            store_rows<N, R>(pY, row0, an);
         }
-        double hx[N];
-        row_times2<N>(a, h, sX, an, hx);  // A X and H X share the loads of X
+        double h[R][N];
+        load_rows<N, R>(sH, row0, h);
         {
-            double t[N];
-            row_times<N, false>(a, sY, t);  // A Y
-#pragma unroll
-            for (int j = 0; j < N; j++) gn[j] = g[j];
-            row_times_T<N>(t, sA, gn);  // G + (A Y) A'
+            double hx[R][N];
+            rows_times<N, R, false>(h, sX, hx);     // H X
+            __syncwarp();                           // every lane has read X: sX now receives H X
+            store_rows<N, R>(sX, row0, hx);
         }
-        {
-            store_row<N>(sS, li, hx);
-            __syncwarp();
-            // H + A' (H X): row i needs column i of A
-            double acol[N];
-#pragma unroll
-            for (int k = 0; k < N; k++) acol[k] = sA[k * LD + li];
-#pragma unroll
-            for (int j = 0; j < N; j++) hn[j] = h[j];
-            row_times<N, true>(acol, sS, hn);
-        }
-        // convergence: ||H+ - H||_F <= tol ||H+||_F, reduced over the team through sRow
+        __syncwarp();
         double d2 = 0.0, h2 = 0.0;
+        {
+            // H_{k+1} = H + A' (H X): row i needs column i of A
+            double acol[R][N], hn[R][N];
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            const double d = hn[j] - h[j];
-            d2 = fma(d, d, d2);
-            h2 = fma(hn[j], hn[j], h2);
-        }
-        sRow[li] = d2;
-        sRow[LD + li] = h2;
-        __syncwarp();
-        double D2 = 0.0, H2 = 0.0;
+            for (int r = 0; r < R; r++)
 #pragma unroll
-        for (int k = 0; k < N; k++) {
-            D2 += sRow[k];
-            H2 += sRow[LD + k];
+                for (int k = 0; k < N; k++) acol[r][k] = pA[k * LD + row0 + r];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int j = 0; j < N; j++) hn[r][j] = h[r][j];
+            rows_times<N, R, true>(acol, sX, hn);
+            // convergence: ||H+ - H||_F <= tol ||H+||_F over the team
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    const double d = hn[r][j] - h[r][j];
+                    d2 = fma(d, d, d2);
+                    h2 = fma(hn[r][j], hn[r][j], h2);
+                }
+            // A team that has converged keeps H frozen while the rest of its warp goes on (its A and G free-run:
+            // they are not outputs), so a system's result never depends on its neighbours in the batch
+            if (!conv) store_rows<N, R>(sH, row0, hn);
         }
-        __syncwarp();
+        const double D2 = team_sum<TEAM>(d2, team_base), H2 = team_sum<TEAM>(h2, team_base);
         if (!conv) {
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                a[j] = an[j];
-                g[j] = gn[j];
-                h[j] = hn[j];
-            }
             iters = it + 1;
             if (D2 <= kDareTol * kDareTol * H2) conv = true;
-            if (!(D2 == D2)) conv = true;  // NaN: stop, reported through info
-            if (!(D2 == D2)) ok = false;
+            if (!(D2 == D2)) {  // NaN: stop, reported through info
+                conv = true;
+                ok = false;
+            }
         }
+        double *tmp = pA;
+        pA = pY;
+        pY = tmp;
     }
 
     // P = (H + H') / 2
-    store_row<N>(sH, li, h);
     __syncwarp();
-    double p[N];
+    double p[R][N];
+    {
+        double h[R][N];
+        load_rows<N, R>(sH, row0, h);
 #pragma unroll
-    for (int j = 0; j < N; j++) p[j] = 0.5 * (h[j] + sH[j * LD + li]);
-    if (!ghost && D.P && li < n) {
+        for (int r = 0; r < R; r++)
 #pragma unroll
-        for (int j = 0; j < N; j++)
-            if (j < n) D.P[sys * (int64_t)n * n + li * n + j] = p[j];
+            for (int j = 0; j < N; j++) p[r][j] = 0.5 * (h[r][j] + sH[j * LD + row0 + r]);
+    }
+    if (!ghost && D.P) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int gi = row0 + r;
+            if (gi < n) {
+#pragma unroll
+                for (int j = 0; j < N; j++)
+                    if (j < n) D.P[sys * (int64_t)n * n + gi * n + j] = p[r][j];
+            }
+        }
     }
 
     // K = (R + B'PB)^-1 B'PA
     {
-        double a0[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) a0[j] = (!ghost && li < n && j < n) ? Ap[li * n + j] : 0.0;
-        __syncwarp();
-        store_row<N>(sA, li, a0);
-        store_row<N>(sS, li, brow);
-        __syncwarp();
-        double pb[N], pa[N];
-        row_times<N, false>(p, sS, pb);  // P B
-        row_times<N, false>(p, sA, pa);  // P A
-        store_row<N>(sX, li, pb);
-        store_row<N>(sY, li, pa);
-        __syncwarp();
-        double bcol[N], w[N], r1[N], r2[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) bcol[k] = sS[k * LD + li];  // column i of B = row i of B'
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            w[j] = (!ghost && li < m && j < m) ? Rp[li * m + j] : (li == j ? 1.0 : 0.0);
-            r2[j] = 0.0;
+        {
+            double a0[R][N], brow[R][N];
+            load_global_rows(Ap, n, n, a0);
+            load_global_rows(Bp, n, m, brow);
+            __syncwarp();  // every lane has read sH (transposed) above
+            store_rows<N, R>(pA, row0, a0);
+            store_rows<N, R>(pY, row0, brow);
         }
-        row_times<N, true>(bcol, sX, w);    // R + B'(PB)
-        row_times<N, false>(bcol, sY, r1);  // B'(PA)
         __syncwarp();
-        ok &= gauss_jordan<N, false>(w, r1, r2, sRow, sG, sH, li, team_base);  // K rows -> sG
-        if (!ghost && D.K && li < m) {
+        {
+            double pb[R][N];
+            rows_times<N, R, false>(p, pY, pb);  // P B
+            store_rows<N, R>(sX, row0, pb);
+        }
+        {
+            double pa[R][N];
+            rows_times<N, R, false>(p, pA, pa);  // P A
+            store_rows<N, R>(sH, row0, pa);
+        }
+        __syncwarp();
+        double bcol[R][N], w[R][N], r1[R][N], r2[R][N];
 #pragma unroll
-            for (int j = 0; j < N; j++)
-                if (j < n) D.K[sys * (int64_t)m * n + li * n + j] = sG[li * LD + j];
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int k = 0; k < N; k++) bcol[r][k] = pY[k * LD + row0 + r];  // column i of B = row i of B'
+        load_R_pad(w);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++) r2[r][j] = 0.0;
+        rows_times<N, R, true>(bcol, sX, w);    // R + B'(PB)
+        rows_times<N, R, false>(bcol, sH, r1);  // B'(PA)
+        __syncwarp();
+        ok &= gauss_jordan<N, R, false>(w, r1, r2, sRow, pA, pY, li, team_base);  // K rows -> pA
+        if (!ghost && D.K) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int gi = row0 + r;
+                if (gi < m) {
+#pragma unroll
+                    for (int j = 0; j < N; j++)
+                        if (j < n) D.K[sys * (int64_t)m * n + gi * n + j] = pA[gi * LD + j];
+                }
+            }
         }
     }
+    // the pivot / NaN tests are evaluated identically by every lane of a team: lane 0 reports
     if (!ghost && li == 0) {
         D.iters[sys] = iters;
         D.info[sys] = !ok ? 2 : (conv ? 0 : 1);
@@ -443,15 +634,16 @@ __global__ void dare_validate_kernel(const __grid_constant__ DareArgs D) {
     D.iters[sys] = 0;
 }
 
-template <int N>
+template <int N, int R>
 static cudaError_t launch_dare(const DareArgs &D, cudaStream_t st) {
-    using L = Lay<N>;
-    const size_t smem = (size_t)kDareWarps * L::SLOTS * L::TEAM * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(dare_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    using L = Lay<N, R>;
+    constexpr int WARPS = DareCfg<N, R>::WARPS;
+    const size_t smem = (size_t)WARPS * L::SLOTS * L::BLOCK * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(dare_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int64_t per_block = (int64_t)kDareWarps * L::TEAMS;
+    const int64_t per_block = (int64_t)WARPS * L::TEAMS;
     const int64_t blocks = (D.batch + per_block - 1) / per_block;
-    dare_kernel<N><<<(unsigned)blocks, kDareWarps * 32, smem, st>>>(D);
+    dare_kernel<N, R><<<(unsigned)blocks, WARPS * 32, smem, st>>>(D);
     return cudaGetLastError();
 }
 
@@ -503,11 +695,12 @@ extern "C" int qt_dare_batched(qt_context *ctx, int32_t n, int32_t m, int64_t ba
     if (rc) return rc;
     const int need = n > m ? n : m;
     cudaError_t err;
-    if (need <= 4) err = launch_dare<4>(D, ctx->stream);
-    else if (need <= 6) err = launch_dare<6>(D, ctx->stream);
-    else if (need <= 9) err = launch_dare<9>(D, ctx->stream);
-    else if (need <= 12) err = launch_dare<12>(D, ctx->stream);
-    else err = launch_dare<16>(D, ctx->stream);
+    // <padded size N, rows per lane R>: lanes per system N / R, systems per warp 32 / (N / R)
+    if (need <= 4) err = launch_dare<4, 2>(D, ctx->stream);          // 2 lanes, 16 systems per warp
+    else if (need <= 6) err = launch_dare<6, QT_DARE_R6>(D, ctx->stream);
+    else if (need <= 9) err = launch_dare<QT_DARE_N9, QT_DARE_R9>(D, ctx->stream);
+    else if (need <= 12) err = launch_dare<12, QT_DARE_R12>(D, ctx->stream);
+    else err = launch_dare<16, QT_DARE_R16>(D, ctx->stream);
     if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "dare_kernel launch", cudaGetErrorString(err));
     ctx->launches += 1;
     return QT_OK;

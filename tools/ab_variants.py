@@ -2,7 +2,9 @@
 and, on the GPU box, time the headline rollout with each:
 
     python tools/ab_variants.py build  name1:-DQT_X=0  name2:-DQT_Y=1,-DQT_Z=0 ...
+    python tools/ab_variants.py build  only=qt_dare.cu  name1:-DQT_X=0 ...   # recompile one source, link the default objects of the rest
     python tools/ab_variants.py run [E]      # every variants/libqtrack_*.so + the default library
+    python tools/ab_variants.py run_dare [batch]
 """
 import os
 import pathlib
@@ -17,6 +19,11 @@ sys.path.insert(0, str(ROOT))
 def build(specs):
     from lqr_quadcopter_test_b200 import build as qb
 
+    only = None
+    if specs and specs[0].startswith("only="):
+        only = specs[0][5:].split(",")
+        specs = specs[1:]
+        qb.build()                       # default objects of the other sources
     VAR.mkdir(exist_ok=True)
     for old in VAR.glob("libqtrack_*.so"):
         old.unlink()
@@ -28,14 +35,19 @@ def build(specs):
         tmp = VAR / f"obj_{name}"
         tmp.mkdir(exist_ok=True)
         procs = []
+        mine = []
         for src in qb.SOURCES:
+            if only is not None and src not in only:
+                objs.append(str(qb.PKG / "build" / (src + ".o")))
+                continue
             o = tmp / (src + ".o")
             objs.append(str(o))
+            mine.append(str(o))
             procs.append(subprocess.Popen([nvcc, *qb.NVCC_FLAGS, *flags, "-c", str(qb.CSRC / src), "-o", str(o)]))
         assert all(p.wait() == 0 for p in procs), name
         subprocess.run([nvcc, "-shared", "-o", str(VAR / f"libqtrack_{name}.so"), *objs, "-gencode",
                         "arch=compute_100a,code=sm_100a"], check=True)
-        for o in objs:
+        for o in mine:
             os.unlink(o)
         tmp.rmdir()
         print("built", name, flags, flush=True)
@@ -109,6 +121,11 @@ def one(E):
     print("   ".join(res))
 
 
+def one_dare(batch):
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_dare.py"), str(batch), "brief"], capture_output=True, text=True)
+    print(r.stdout.strip().replace("\n", "   ") or r.stderr[-400:])
+
+
 MODE = "one"
 
 if __name__ == "__main__":
@@ -119,6 +136,11 @@ if __name__ == "__main__":
     elif sys.argv[1] == "run_policy":
         MODE = "one_policy"
         run(int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18)
+    elif sys.argv[1] == "run_dare":
+        MODE = "one_dare"
+        run(int(sys.argv[2]) if len(sys.argv) > 2 else 65536)
+    elif sys.argv[1] == "one_dare":
+        one_dare(int(sys.argv[2]))
     elif sys.argv[1] == "one_policy":
         one_policy(int(sys.argv[2]))
     else:
