@@ -18,7 +18,12 @@ scaling: every rank gets its own 2^20 episodes (seeds disjoint).  Prints ONE JSO
              (MEASURED_PEAKS.json has no FP64 figure); HBM numbers are given for context
   cpu_baseline  the CPU oracle (C restatement of the reference's loop, all host threads) on a bounded
              sample of the same workload — a reported baseline, not the optimisation target
-  dare       batched DARE throughput (second headline metric): 65 536 n=6 systems per launch
+  dare       batched DARE throughput (second headline metric): 65 536 systems per GPU for n = 6 (LQR), n = 9 (LQI) and
+             the 12 x 4 / 15 x 4 sizes the north star names; device-resident, through the host-buffer call qt_dare_host
+             (e2e), summed over the ranks, next to scipy's solve_discrete_are + gain on this box (1 core and all cores)
+  strong     the literal BASELINE configs at FIXED total size split over the N ranks: config 2 (2^20 episodes), config 4
+             (65 536 candidates x 64 episodes end to end INCLUDING candidate sampling), config 5 (2^22-episode teacher
+             data set, stride 10)
   policy     SURVEY §8(f).2: the same closed loop driven by the 64-64 deep tracking policy (fp32 network in
              the kernel) on 2^17 episodes, with the Riccati supervisor labelling every 10th step
 """
@@ -159,6 +164,75 @@ def sized_cpu_sample(target_seconds: float, n_threads: int) -> int:
     return max(n_threads, min(episodes, 1 << 16))
 
 
+
+def python_reference_timing(cores: int, timeout_s: float = 240.0) -> dict:
+    """The UNMODIFIED Python reference (baseline/_ref, see baseline/install_reference.py) timed on this box's host
+    cores: Evaluator.evaluate(10, 42), solve_dare x 1000, _evaluate_config 8 x 5 — BASELINE.md §3."""
+    script = ROOT / "baseline" / "time_reference.py"
+    if not (ROOT / "baseline" / "_ref" / "quadcopter_tracking").is_dir():
+        return {"unavailable": "baseline/_ref is not installed (python baseline/install_reference.py needs /root/reference)"}
+    try:
+        r = subprocess.run([sys.executable, str(script), "--procs", str(cores)], capture_output=True, text=True,
+                           timeout=timeout_s, cwd=tempfile.gettempdir())
+        if r.returncode != 0:
+            return {"unavailable": (r.stderr or r.stdout).strip().splitlines()[-1][:300]}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        out["what"] = ("quadcopter_tracking 0.5.0 imported unmodified from baseline/_ref: Evaluator.evaluate(10 episodes, seed 42, "
+                       "riccati_lqr, stationary) on 1 core and in N processes on disjoint seeds; solve_dare over sampled tuning-range "
+                       "(Q, R); ControllerTuner._evaluate_config for 8 candidates x 5 episodes (one candidate per process)")
+        return out
+    except (subprocess.TimeoutExpired, ValueError, IndexError, OSError) as exc:
+        return {"unavailable": repr(exc)[:300]}
+
+
+def _scipy_dare_worker(args):
+    """solve_dare (validation + scipy.linalg.solve_discrete_are + gain) on `count` tuning-range systems of size n."""
+    n, count, seed = args
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    import numpy as np
+
+    import oracle
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    from bench_dare import dare_test_systems
+
+    if n in (6, 9):
+        A, B = oracle.build_systems_reference(lqi=(n == 9))
+        rng = np.random.default_rng(seed)
+        q = rng.uniform([5e-5, 5e-5, 10, 1e-3, 1e-3, 2], [5e-4, 5e-4, 25, 1e-2, 1e-2, 8], (count, 6))
+        if n == 9:
+            q = np.concatenate([q, rng.uniform([1e-3, 1e-3, 1e-2], [0.1, 0.1, 1.0], (count, 3))], axis=1)
+        Q = np.stack([np.diag(x) for x in q])
+        R = np.stack([np.diag(x) for x in rng.uniform(0.5, 2.0, (count, 4))])
+    else:
+        A, B, Q, R = dare_test_systems(n, 4, count, seed)
+    oracle.solve_dare_reference(A, B, Q[0], R[0])
+    t0 = time.perf_counter()
+    for i in range(count):
+        oracle.validate_reference(Q[i], R[i])
+        oracle.solve_dare_reference(A, B, Q[i], R[i])
+    return count, time.perf_counter() - t0
+
+
+def scipy_dare_rates(n: int, cores: int, count: int = 400) -> dict:
+    """The reference's DARE path (scipy) on this box: one core, and all cores (one process per core)."""
+    import multiprocessing as mp
+
+    c1, t1 = _scipy_dare_worker((n, count, 0))
+    procs = max(1, cores)
+    per = max(50, count // 4)
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_scipy_dare_worker, [(n, 2, 0)] * procs)          # imports outside the timed region
+        t0 = time.perf_counter()
+        res = pool.map(_scipy_dare_worker, [(n, per, 1 + p) for p in range(procs)])
+        wall = time.perf_counter() - t0
+    return {"value": sum(r[0] for r in res) / wall, "unit": "solves/s", "cores": procs, "kind": "reference",
+            "single_core_value": c1 / t1,
+            "sample": f"scipy.linalg.solve_discrete_are + validation + gain (the reference's solve_dare, riccati_lqr.py:119-184) on "
+                      f"{per} n={n} systems per process x {procs} processes ({wall:.1f} s); single core: {count} systems"}
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -180,12 +254,209 @@ def run_reference_arm(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, EPISODES_PER_GPU),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_timing(cores)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "The reference itself is single-threaded Python (~4.5e3 env-steps/s/core, BASELINE.md); it cannot "
-                "travel to the GPU box, so this arm times its C restatement, a far stronger CPU baseline.",
+        "note": "`value` is the C restatement of the reference's loop (oracle/qt_oracle.c) on all host threads: ~1000x faster per "
+                "core than the reference itself, i.e. the stronger baseline.  The unmodified Python reference, shipped in "
+                "baseline/_ref, is timed in the same run: cpu_baseline.python_reference.",
     }
     emit(line)
+
+
+
+DARE_SIZES = ((6, 65536), (9, 65536), (12, 16384), (15, 16384))   # (n, systems per GPU); m = 4 throughout
+
+
+def run_dare_section(ctx, rank: int, world: int, fp64_tflops: float, barrier) -> dict:
+    """Batched DARE throughput, every rank solving its own batch (weak scaling, no collective in the data path)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    from bench_dare import dare_test_systems
+
+    dev = ctx.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = {"metric": "batched DARE solves/s (validation + structure-preserving doubling + gain), summed over the ranks",
+           "unit": "solves/s", "sizes": {}}
+    for n, batch in DARE_SIZES:
+        rng = np.random.default_rng(42 + rank)
+        if n <= 9:    # the reference's own designs on the tuning ranges (tuning_riccati.yaml), built on the device
+            q = rng.uniform([5e-5, 5e-5, 10, 1e-3, 1e-3, 2], [5e-4, 5e-4, 25, 1e-2, 1e-2, 8], (batch, 6))
+            if n == 9:
+                q = np.concatenate([q, rng.uniform([1e-3, 1e-3, 1e-2], [0.1, 0.1, 1.0], (batch, 3))], axis=1)
+            r = rng.uniform(0.5, 2.0, (batch, 4))
+            A, B = torch.empty((n, n), **f64), torch.empty((n, 4), **f64)
+            Q, R = torch.empty((batch, n, n), **f64), torch.empty((batch, 4, 4), **f64)
+            ctx.build_lqr_systems(n, batch, 0.01, 1.0, 9.81, torch.as_tensor(q, **f64), torch.as_tensor(r, **f64), A, B, Q, R)
+            what = "reference design (diagonal Q/R of the tuning ranges)"
+        else:         # the 12 x 4 / 15 x 4 sizes the north star names: integrator chains, dense SPD Q
+            A, B, Q, R = (torch.as_tensor(x, **f64) for x in dare_test_systems(n, 4, batch, seed=rank))
+            what = "synthetic dense system (integrator chain with random coupling, dense SPD Q, diagonal R)"
+        K = torch.empty((batch, 4, n), **f64)
+        iters = torch.zeros(batch, dtype=torch.int32, device=dev)
+        info = torch.zeros(batch, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            ctx.dare_batched(n, 4, batch, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        d0.record()
+        for _ in range(reps):
+            ctx.dare_batched(n, 4, batch, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
+        d1.record()
+        barrier()
+        ms = d0.elapsed_time(d1) / reps
+        # e2e: pinned host matrices in, host gains / info out, through the C ABI (qt_dare_host)
+        Ah, Bh, Qh, Rh = (t.cpu().pin_memory() for t in (A, B, Q, R))
+        Kh = torch.empty((batch, 4, n), dtype=torch.float64).pin_memory()
+        ih, fh = torch.empty(batch, dtype=torch.int32).pin_memory(), torch.empty(batch, dtype=torch.int32).pin_memory()
+        ctx.dare_host(n, 4, batch, Ah, 0, Bh, 0, Qh, n * n, Rh, 16, None, Kh, ih, fh)
+        barrier()
+        e_reps = 5
+        w0 = time.perf_counter()
+        for _ in range(e_reps):
+            ctx.dare_host(n, 4, batch, Ah, 0, Bh, 0, Qh, n * n, Rh, 16, None, Kh, ih, fh)
+        barrier()
+        e2e_s = (time.perf_counter() - w0) / e_reps
+        same = bool(torch.equal(Kh, K.cpu()))
+        t = torch.tensor([ms, e2e_s * 1e3], **f64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0].item()), float(t[1].item())
+        k = float(iters.double().mean().item())
+        rate = world * batch / (ms * 1e-3)
+        tflops = rate * w_dare(n, 4, k) / 1e12
+        out["sizes"][f"n{n}"] = {
+            "n": n, "m": 4, "systems": what, "batch_per_gpu": batch, "value": rate, "ms_per_launch": ms,
+            "mean_doubling_iterations": k, "failed": int((info != 0).sum().item()),
+            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "solves/s", "api": "qt_dare_host (C ABI, pinned host buffers)",
+                    "h2d_bytes_per_step": 8 * (n * n + 4 * n + batch * (n * n + 16)), "d2h_bytes_per_step": batch * (8 * 4 * n + 8),
+                    "matches_device_resident_result": same},
+            "roofline": {"bound": "fp64", "achieved": tflops, "peak": world * fp64_tflops, "unit": "TFLOP/s",
+                         "frac": tflops / (world * fp64_tflops) if fp64_tflops > 0 else None,
+                         "flops_per_solve": w_dare(n, 4, k)}}
+    head = out["sizes"]["n6"]
+    out.update({"value": head["value"], "batch": head["batch_per_gpu"], "ms_per_launch": head["ms_per_launch"],
+                "mean_doubling_iterations": head["mean_doubling_iterations"], "failed": head["failed"], "e2e": head["e2e"],
+                "roofline": head["roofline"], "n_gpus": world})
+    return out
+
+
+def run_strong_section(ctx, rank: int, world: int, barrier, args) -> dict:
+    """The literal BASELINE configs at fixed TOTAL size, split over the ranks (strong scaling; the driver's SCALE file
+    holds this object at every N)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lqr_quadcopter_test_b200 import ControllerTuner, GainSearchSpace, RiccatiLQRController, SuccessCriteria, TuningConfig
+    from lqr_quadcopter_test_b200 import dist as qd
+    from lqr_quadcopter_test_b200.config import EnvConfig
+
+    if args.no_strong:
+        return {"skipped": "--no-strong"}
+    dev = ctx.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = {"scaling": "strong", "n_gpus": world}
+
+    def max_over_ranks(seconds: float) -> float:
+        t = torch.tensor([seconds], **f64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def median_wall(fn, reps=3):
+        fn()                                                  # warm-up
+        ts = []
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(max_over_ranks(time.perf_counter() - t0))
+        return sorted(ts)[len(ts) // 2]
+
+    # config 2: 2^20 episodes in total, linear target, Riccati-LQR defaults: reset + rollout + summary (+ all_gather)
+    total2 = int(args.strong_episodes)
+    lo, hi = qd.shard_range(total2, rank, world)
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    ctrl = RiccatiLQRController(config={})
+    prm = ctrl.kernel_params(env, SuccessCriteria())
+    K = torch.as_tensor(np.ascontiguousarray(ctrl.K), **f64)
+    E = hi - lo
+    seeds = torch.arange(lo, hi, dtype=torch.int64, device=dev) + 42
+    s0, tp, met, sums = torch.empty((12, E), **f64), torch.empty((12, E), **f64), torch.empty((16, E), **f64), torch.zeros(16, **f64)
+
+    def config2():
+        ctx.reset_batched(prm, seeds, s0, tp)
+        ctx.rollout(prm, E, STEPS_PER_EPISODE + 2, 1, s0, tp, K, 6, E, met)
+        ctx.reduce_summary(met, E, sums)
+        if world > 1:
+            qd.reduce_summary_across_ranks(sums, lo)
+        else:
+            sums.cpu()
+
+    sec = median_wall(config2)
+    out["config2"] = {"workload": f"{total2} episodes in total, linear target, Riccati-LQR, 3000 steps; reset + rollout + summary "
+                                  "reduction (+ all_gather of 17 doubles per rank)", "episodes_per_gpu": E, "seconds": sec,
+                      "env_steps_per_s": total2 * STEPS_PER_EPISODE / sec}
+    del s0, tp, met
+
+    # config 4: 65 536 candidates x 64 episodes, end to end from the generator seed to host score rows
+    C = int(args.strong_candidates)
+    space = GainSearchSpace(q_pos_range=([5e-5, 5e-5, 10.0], [5e-4, 5e-4, 25.0]), q_vel_range=([1e-3, 1e-3, 2.0], [1e-2, 1e-2, 8.0]),
+                            r_controls_range=([0.5] * 4, [2.0] * 4))
+
+    def config4():
+        tuner = ControllerTuner(TuningConfig(controller_type="riccati_lqr", search_space=space, strategy="random", max_iterations=C,
+                                             evaluation_episodes=64, evaluation_horizon=3000, seed=42,
+                                             output_dir=os.path.join(tempfile.gettempdir(), f"qt_bench_tuning_{rank}")))
+        block, rows = tuner.sweep(C)
+        config4.best = float(rows[0].max())
+
+    sec = median_wall(config4)
+    out["config4"] = {"workload": f"{C} Q/R candidates x 64 episodes x 3000 steps (stationary target): candidate sampling (host rng, "
+                                  "the reference's stream) + H2D + DARE + reset + rollout with fused per-candidate scores + D2H "
+                                  "(+ all_gather of score and parameter rows)", "seconds": sec, "candidates_per_s": C / sec,
+                      "dare_solves_per_s_end_to_end": C / sec, "env_steps_per_s": C * 64 * 3000 / sec, "best_score": config4.best}
+
+    # config 5: teacher data set, 2^22 episodes in total at stride 10 (300 rows of 18 + 4 fp32 per episode = 111 GB in
+    # all), produced chunk by chunk into buffers the consumer re-uses (SURVEY §8(d): "produced in chunks as torch tensors")
+    total5 = int(args.strong_dataset_episodes)
+    lo5, hi5 = qd.shard_range(total5, rank, world)
+    n_chunks = max(1, -(-(hi5 - lo5) // (1 << 20)))
+    chunk = -(-(hi5 - lo5) // n_chunks)
+    env5 = EnvConfig()
+    env5.target.motion_type = "linear"
+    slots = (STEPS_PER_EPISODE + 9) // 10
+    buffers: dict = {}
+
+    def buffers_for(n):          # one set per chunk size (the last chunk of an uneven shard is shorter)
+        if n not in buffers:
+            buffers[n] = (torch.empty((slots, n, 18), dtype=torch.float32, device=dev),
+                          torch.empty((slots, n, 4), dtype=torch.float32, device=dev),
+                          torch.empty((12, n), **f64), torch.empty((12, n), **f64), torch.empty((16, n), **f64))
+        return buffers[n]
+
+    def config5():
+        for c0 in range(lo5, hi5, chunk):
+            n = min(chunk, hi5 - c0)
+            feat, act, s0_, tp_, met_ = buffers_for(n)
+            sd = torch.arange(c0, c0 + n, dtype=torch.int64, device=dev) + 42
+            ctx.reset_batched(prm5, sd, s0_, tp_)
+            ctx.rollout(prm5, n, STEPS_PER_EPISODE, 1, s0_, tp_, K, 6, n, met_, None, None, None, 1, 0, feat, act, 10, slots)
+
+    prm5 = ctrl.kernel_params(env5, SuccessCriteria())
+    sec = median_wall(config5, reps=2)
+    rows = total5 * slots
+    out["config5"] = {"workload": f"{total5} episodes in total, teacher data set every 10th step (18 + 4 fp32 per row), chunks of "
+                                  f"{chunk} episodes into re-used device buffers", "seconds": sec, "rows_per_s": rows / sec,
+                      "write_gbs": rows * 88 / sec / 1e9, "env_steps_per_s": total5 * STEPS_PER_EPISODE / sec}
+    return out
 
 
 def ctx_sm_count(ctx) -> int:
@@ -285,13 +556,17 @@ def run_gpu_arm(args) -> None:
     e2e_value = float(metrics_host[0].sum().item()) * e2e_steps * world / float(e2e_t.item())
     same = bool(torch.equal(metrics_host, metrics.cpu()))
 
+    # ---- collective secondary sections (every rank takes part; times are max over ranks) ---------------
+    fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
+    dare_section = run_dare_section(ctx, rank, world, fp64_tflops, barrier)
+    strong = run_strong_section(ctx, rank, world, barrier, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- rank 0 only: roofline denominators, DARE throughput, CPU baseline --------------------------
-    fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
+    # ---- rank 0 only: roofline of the headline kernel, policy section, CPU baselines --------------------
     k_ms = statistics.mean(kernel_ms)
     steps_per_launch = steps_per_pass
     Kh = np.asarray(ctrl.K)
@@ -330,37 +605,7 @@ def run_gpu_arm(args) -> None:
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
 
-    # DARE: 65 536 candidates of the n=6 design (tuning_riccati.yaml ranges), matrices resident
-    rng = np.random.default_rng(42)
-    q = rng.uniform([5e-5, 5e-5, 10, 1e-3, 1e-3, 2], [5e-4, 5e-4, 25, 1e-2, 1e-2, 8], (DARE_BATCH, 6))
-    r = rng.uniform(0.5, 2.0, (DARE_BATCH, 4))
-    qd_, rd_ = torch.as_tensor(q, **f64), torch.as_tensor(r, **f64)
-    A, B = torch.empty((6, 6), **f64), torch.empty((6, 4), **f64)
-    Q, R = torch.empty((DARE_BATCH, 6, 6), **f64), torch.empty((DARE_BATCH, 4, 4), **f64)
-    ctx.build_lqr_systems(6, DARE_BATCH, 0.01, 1.0, 9.81, qd_, rd_, A, B, Q, R)
-    Kd = torch.empty((DARE_BATCH, 4, 6), **f64)
-    iters = torch.zeros(DARE_BATCH, dtype=torch.int32, device=dev)
-    info = torch.zeros(DARE_BATCH, dtype=torch.int32, device=dev)
-    for _ in range(3):
-        ctx.dare_batched(6, 4, DARE_BATCH, A, 0, B, 0, Q, 36, R, 16, None, Kd, iters, info)
-    torch.cuda.synchronize()
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    d0.record()
-    for _ in range(reps):
-        ctx.dare_batched(6, 4, DARE_BATCH, A, 0, B, 0, Q, 36, R, 16, None, Kd, iters, info)
-    d1.record()
-    torch.cuda.synchronize()
-    dare_ms = d0.elapsed_time(d1) / reps
-    mean_iters = float(iters.double().mean().item())
-    dare_rate = DARE_BATCH / (dare_ms * 1e-3)
-    dare_tflops = dare_rate * w_dare(DARE_N, 4, mean_iters) / 1e12
-    dare = {"metric": "batched DARE solves/s (n=6, m=4, validation + solve + gain)", "value": dare_rate,
-            "unit": "solves/s", "batch": DARE_BATCH, "ms_per_launch": dare_ms, "mean_doubling_iterations": mean_iters,
-            "failed": int((info != 0).sum().item()),
-            "roofline": {"bound": "fp64", "achieved": dare_tflops, "peak": fp64_tflops, "unit": "TFLOP/s",
-                         "frac": dare_tflops / fp64_tflops if fp64_tflops > 0 else None,
-                         "flops_per_solve": w_dare(DARE_N, 4, mean_iters)}}
+    dare = dare_section
 
     # deep policy in the loop (random-init 64-64 network, torch seed 0; linear target; labels every 10th step)
     policy = None
@@ -384,14 +629,16 @@ def run_gpu_arm(args) -> None:
         p_ms = statistics.median(pev[i].elapsed_time(pev[i + 1]) for i in range(5))   # secondary figure: median of five
         p_steps = float(pout["metrics"][0].sum().item())
         fma_per_step = 18 * 64 + 64 * 64 + 64 * 4
-        fp32_peak = ctx_sm_count(ctx) * 128 * 2 * (clock_info.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        fp32_nominal = ctx_sm_count(ctx) * 128 * 2 * (clock_info.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        fp32_peak, _ = ctx.fp32_peak_probe(1 << 17)        # measured: register-resident FFMA chains, this run
         policy = {"metric": "closed-loop env-steps/s with the 64-64 deep tracking policy acting (fp32, in-kernel)",
                   "value": p_steps / (p_ms * 1e-3), "unit": "env-steps/s", "episodes": Ep, "ms_per_launch": p_ms,
                   "includes": "reset + rollout + supervisor labels and 18+4 fp32 data-set rows every 10th step",
                   "roofline": {"bound": "fp32", "achieved": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12,
                                "peak": fp32_peak, "unit": "TFLOP/s",
                                "frac": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12 / fp32_peak,
-                               "peak_source": "nominal: SMs x 128 FP32 lanes x 2 x max SM clock (no measured FP32 figure)",
+                               "peak_source": "register-resident FFMA probe (qt_fp32_peak_probe) in this run",
+                               "nominal_peak": fp32_nominal,
                                "algorithmic_flops_per_env_step": 2 * fma_per_step}}
     except Exception as exc:  # the headline line must not be lost to the secondary section
         policy = {"error": repr(exc)}
@@ -404,8 +651,15 @@ def run_gpu_arm(args) -> None:
         "value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
         "sample": f"{sample_eps} of the 2^20 episodes x 3000 steps ({cpu_s:.1f} s), oracle/qt_oracle.c on {cores} threads",
         "single_core_value": cpu1_rate,
-        "python_reference_note": "the Python reference measured 4.5e3 env-steps/s on one core (BASELINE.md §2)",
+        "python_reference": python_reference_timing(cores) if world == 1 else {"skipped": "timed at N=1 only"},
     }
+    if world == 1:
+        for n_key, entry in dare["sizes"].items():
+            try:
+                entry["cpu_baseline"] = scipy_dare_rates(int(n_key[1:]), cores)
+            except Exception as exc:
+                entry["cpu_baseline"] = {"error": repr(exc)[:200]}
+        dare["cpu_baseline"] = dare["sizes"]["n6"].get("cpu_baseline")
 
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -414,9 +668,9 @@ def run_gpu_arm(args) -> None:
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * E + 4 * 6 * 8,
                 "d2h_bytes_per_step": 16 * 8 * E, "api": "qt_evaluate_host (C ABI, pinned host buffers)",
-                "matches_device_resident_result": same},
+                "matches_device_resident_result": same, "fraction_of_device_timed_value": e2e_value / value},
         "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare, "policy": policy,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "dare": dare, "strong": strong, "policy": policy,
     }
     emit(line)
     if world > 1:
@@ -449,6 +703,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["qtrack", "reference"], default="qtrack")
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU (default 2^20)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total-size (strong scaling) section")
+    ap.add_argument("--strong-episodes", type=int, default=1 << 20, help="config 2: total episodes over all ranks")
+    ap.add_argument("--strong-candidates", type=int, default=65536, help="config 4: total candidates over all ranks")
+    ap.add_argument("--strong-dataset-episodes", type=int, default=1 << 22, help="config 5: total episodes over all ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

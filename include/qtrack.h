@@ -382,6 +382,10 @@ int qt_sqrt_pair_probe(qt_context *ctx, int64_t n, const double *a_dev, const do
 int qt_fp64_peak_probe(qt_context *ctx, int64_t iters, double *tflops_out_host,
                        double *ms_out_host);
 
+/* The same for the FP32 pipe (register-resident FFMA chains): denominator of the policy kernel's roofline. */
+int qt_fp32_peak_probe(qt_context *ctx, int64_t iters, double *tflops_out_host,
+                       double *ms_out_host);
+
 #ifdef __cplusplus
 }
 #endif

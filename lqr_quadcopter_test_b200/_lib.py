@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "qt_step_batched", "qt_rollout", "qt_dare_batched", "qt_build_lqr_systems",
     "qt_reduce_scores", "qt_reduce_summary", "qt_evaluate_host", "qt_fp64_peak_probe",
     "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy", "qt_sqrt_pair_probe",
-    "qt_fill_seeds", "qt_rollout_sweep", "qt_dare_host", "qt_sweep_host",
+    "qt_fill_seeds", "qt_rollout_sweep", "qt_dare_host", "qt_sweep_host", "qt_fp32_peak_probe",
 )
 
 _lib = None
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
             "qt_dare_host": (C.c_int, [vp, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp]),
             "qt_sweep_host": (C.c_int, [vp, PP, i32, i64, i64, C.c_uint64, i64, vp, vp, dbl, dbl, vp, vp, vp]),
             "qt_fp64_peak_probe": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]),
+            "qt_fp32_peak_probe": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(dbl)]),
             "qt_sqrt_pair_probe": (C.c_int, [vp, i64, vp, vp, vp, vp]),
             "qt_mlp_packed_floats": (i64, [C.POINTER(QtMlp)]),
             "qt_policy_action_batched": (C.c_int, [vp, C.POINTER(QtMlp), i64, vp, vp]),
@@ -253,6 +254,11 @@ class Context:
             self.handle, C.byref(params), E, max_steps, _ptr(state0), _ptr(tparams), C.byref(mlp),
             _ptr(teacher_K), k_cols, k_stride, _ptr(metrics_out), _ptr(final_state_out), _ptr(traj_out),
             traj_stride, traj_slots, _ptr(feat_out), _ptr(act_out), data_stride, data_slots))
+
+    def fp32_peak_probe(self, iters: int = 1 << 16) -> tuple[float, float]:
+        tf, ms = C.c_double(), C.c_double()
+        self.check(self.lib.qt_fp32_peak_probe(self.handle, iters, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
 
     def fp64_peak_probe(self, iters: int = 1 << 16) -> tuple[float, float]:
         tf, ms = C.c_double(), C.c_double()

@@ -362,6 +362,51 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int64_t iters, double s
 }
 }  // namespace qt
 
+// The same for the FP32 pipe (denominator of the policy kernel's roofline): 16 independent FFMA chains per thread.
+namespace qt {
+constexpr int kProbeChains32 = 16;
+__global__ void __launch_bounds__(256) fp32_probe_kernel(int64_t iters, float seed, float *sink) {
+    float acc[kProbeChains32];
+#pragma unroll
+    for (int i = 0; i < kProbeChains32; i++) acc[i] = seed + (float)(threadIdx.x + i);
+    const float a = 1.0000001f, b = 1e-7f;
+    for (int64_t k = 0; k < iters; k++) {
+#pragma unroll
+        for (int i = 0; i < kProbeChains32; i++) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kProbeChains32; i++) s += acc[i];
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the loop alive
+}
+}  // namespace qt
+
+extern "C" int qt_fp32_peak_probe(qt_context *ctx, int64_t iters, double *tflops_out_host, double *ms_out_host) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, iters > 0 && tflops_out_host, "bad argument");
+    DeviceGuard guard(ctx->device);
+    const int threads = 256, blocks = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    QT_CUDA_TRY(ctx, cudaEventCreate(&e0));
+    QT_CUDA_TRY(ctx, cudaEventCreate(&e1));
+    float *sink = reinterpret_cast<float *>(ctx->partials_dev);
+    fp32_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(iters / 8 + 1, 1.0f, sink);  // warm-up
+    QT_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    fp32_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, 1.0f, sink);
+    QT_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    QT_CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    int rc = check_launch(ctx, "fp32_probe_kernel");
+    ctx->launches += 1;
+    float ms = 0.f;
+    QT_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * (double)kProbeChains32 * (double)iters * (double)threads * (double)blocks;
+    *tflops_out_host = flops / ((double)ms * 1e-3) / 1e12;
+    if (ms_out_host) *ms_out_host = (double)ms;
+    return rc;
+}
+
 extern "C" int qt_fp64_peak_probe(qt_context *ctx, int64_t iters, double *tflops_out_host,
                                   double *ms_out_host) {
     if (!ctx) return QT_ERR_ARG;
