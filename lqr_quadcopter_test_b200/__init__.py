@@ -9,14 +9,18 @@ include/qtrack.h); this package is the thin host layer.  There is no CPU fallbac
 """
 from .config import (EnvConfig, LoggingParams, QuadcopterParams, SimulationParams, TargetParams)
 from .config import SuccessCriteria as EnvSuccessCriteria
-from .controller import (ACTION_KEYS, BaseController, LQRController, PIDController, RiccatiLQRController,
+from .controller import (ACTION_KEYS, DEFAULT_ACTION_LIMITS, ActionLimits, BaseController, LQRController, PIDController,
+                         RiccatiLQRController, validate_action,
                          build_augmented_lqi_system, build_linearized_system, heuristic_lqr_gain,
                          solve_dare, solve_dare_batched)
 from .env import BatchedQuadcopterEnv, QuadcopterEnv
 from .policy import DeepTrackingPolicy, create_controller_from_config, make_policy_network
 from .train import Trainer, TrainingConfig, load_checkpoint_and_resume
 from .eval import Evaluator, load_controller, rollout_device, run_hyperparameter_sweep
-from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, format_metrics_report)
+from .metrics import (EpisodeMetrics, EvaluationSummary, SuccessCriteria, compute_control_effort, compute_episode_metrics,
+                      compute_evaluation_summary, compute_on_target_ratio, compute_tracking_error, detect_overshoots,
+                      format_metrics_report)
+from .target_motion import (CircularMotion, Figure8Motion, LinearMotion, SinusoidalMotion, StationaryMotion, TargetMotion)
 from .tuning import ControllerTuner, GainSearchSpace, TuningConfig, TuningResult
 from .dataset import teacher_dataset
 
@@ -31,5 +35,8 @@ __all__ = [
     "solve_dare_batched", "build_linearized_system", "build_augmented_lqi_system",
     "heuristic_lqr_gain", "Evaluator", "load_controller", "rollout_device", "EpisodeMetrics",
     "EvaluationSummary", "format_metrics_report", "ControllerTuner", "GainSearchSpace",
-    "TuningConfig", "TuningResult", "teacher_dataset",
+    "TuningConfig", "TuningResult", "teacher_dataset", "TargetMotion", "LinearMotion", "CircularMotion",
+    "SinusoidalMotion", "Figure8Motion", "StationaryMotion", "ActionLimits", "DEFAULT_ACTION_LIMITS", "validate_action",
+    "compute_tracking_error", "compute_on_target_ratio", "compute_control_effort", "detect_overshoots",
+    "compute_episode_metrics", "compute_evaluation_summary",
 ]

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import logging
 
+from dataclasses import dataclass
+
 import numpy as np
 
 from . import _lib
@@ -168,6 +170,33 @@ def solve_dare(A: np.ndarray, B: np.ndarray, Q: np.ndarray, R: np.ndarray):
 
 
 # --------------------------------------------------------------------------- controllers -----
+@dataclass
+class ActionLimits:
+    """controllers/base.py:32-57"""
+
+    min_thrust: float = 0.0
+    max_thrust: float = 20.0
+    max_rate: float = 3.0
+
+    def clip_action(self, action: dict) -> dict:
+        return {"thrust": np.clip(action["thrust"], self.min_thrust, self.max_thrust),
+                "roll_rate": np.clip(action["roll_rate"], -self.max_rate, self.max_rate),
+                "pitch_rate": np.clip(action["pitch_rate"], -self.max_rate, self.max_rate),
+                "yaw_rate": np.clip(action["yaw_rate"], -self.max_rate, self.max_rate)}
+
+
+DEFAULT_ACTION_LIMITS = ActionLimits()
+
+
+def validate_action(action: dict) -> None:
+    """controllers/base.py:64-81: KeyError for a missing key, TypeError for a non-numeric value."""
+    for key in ACTION_KEYS:
+        if key not in action:
+            raise KeyError(f"Action missing required key: '{key}'")
+        if not isinstance(action[key], (int, float)):
+            raise TypeError(f"Action['{key}'] must be numeric, got {type(action[key]).__name__}")
+
+
 class BaseController:
     """controllers/base.py:83-135"""
 

@@ -176,6 +176,103 @@ def summary_from_sums(sums: np.ndarray, criteria: SuccessCriteria | None, episod
     )
 
 
+# ---- record post-processing (utils/metrics.py:144-390) ---------------------------------------------------------
+# The reference's drivers call these on the per-step records they have just collected; here Evaluator / ControllerTuner
+# never do — their per-episode metrics are accumulated inside the rollout kernel (the 16 rows of enum qt_metric) and
+# reduced by qt_reduce_summary / the fused score epilogue.  The functions below exist for code that already HOLDS an
+# episode record on the host (a list of step dictionaries, e.g. from Evaluator.run_episode or from the reference's own
+# loop) and wants the reference's numbers for it: plain numpy on host data, the same operations in the same order as
+# the reference, nothing of the accelerated path runs through them.
+def compute_tracking_error(quad_positions: np.ndarray, target_positions: np.ndarray) -> np.ndarray:
+    """utils/metrics.py:144-162"""
+    if quad_positions.shape != target_positions.shape:
+        raise ValueError(f"Shape mismatch: quad {quad_positions.shape} vs target {target_positions.shape}")
+    return np.linalg.norm(target_positions - quad_positions, axis=1)
+
+
+def compute_on_target_ratio(tracking_errors: np.ndarray, target_radius: float) -> float:
+    """utils/metrics.py:165-179"""
+    if len(tracking_errors) == 0:
+        return 0.0
+    return float(np.mean(tracking_errors <= target_radius))
+
+
+def compute_control_effort(actions: np.ndarray) -> tuple[float, float]:
+    """utils/metrics.py:182-202: (sum, mean) of the per-step 2-norm of the action vector."""
+    if len(actions) == 0:
+        return 0.0, 0.0
+    mags = np.linalg.norm(actions, axis=1)
+    return float(np.sum(mags)), float(np.mean(mags))
+
+
+def detect_overshoots(tracking_errors: np.ndarray, target_radius: float, window_size: int = 10) -> tuple[int, float]:
+    """utils/metrics.py:205-261: off-target streaks of >= window_size samples that started from an on-target sample
+    (the streaming form of this scan is the overshoot detector inside the rollout kernel, csrc/qt_rollout.cu)."""
+    if len(tracking_errors) < window_size:
+        return 0, 0.0
+    on = tracking_errors <= target_radius
+    count, worst, in_phase, streak, current = 0, 0.0, False, 0, 0.0
+    for i in range(1, len(on)):
+        if on[i - 1] and not on[i]:
+            in_phase, streak, current = True, 1, tracking_errors[i] - target_radius
+        elif in_phase and not on[i]:
+            streak += 1
+            current = max(current, tracking_errors[i] - target_radius)
+        elif in_phase and on[i]:
+            if streak >= window_size:
+                count += 1
+                worst = max(worst, current)
+            in_phase, streak, current = False, 0, 0.0
+    if in_phase and streak >= window_size:
+        count += 1
+        worst = max(worst, current)
+    return count, float(worst)
+
+
+def compute_episode_metrics(episode_data: list[dict], criteria: SuccessCriteria | None = None,
+                            episode_info: dict | None = None) -> EpisodeMetrics:
+    """utils/metrics.py:264-338 for a recorded episode (list of step dictionaries)."""
+    criteria = criteria or SuccessCriteria()
+    if not episode_data:
+        return EpisodeMetrics(success=False, termination_reason="no_data")
+    quad = np.array([d["quadcopter_position"] for d in episode_data])
+    target = np.array([d["target_position"] for d in episode_data])
+    actions = np.array([d["action"] for d in episode_data])
+    times = np.array([d["time"] for d in episode_data])
+    errors = compute_tracking_error(quad, target)
+    ratio = compute_on_target_ratio(errors, criteria.target_radius)
+    total_effort, mean_effort = compute_control_effort(actions)
+    overshoots, max_overshoot = detect_overshoots(errors, criteria.target_radius)
+    duration = float(times[-1]) if len(times) > 0 else 0.0
+    info = episode_info or {}
+    return EpisodeMetrics(
+        episode_duration=duration, on_target_ratio=ratio, mean_tracking_error=float(np.mean(errors)),
+        max_tracking_error=float(np.max(errors)), rms_tracking_error=float(np.sqrt(np.mean(errors ** 2))),
+        total_control_effort=total_effort, mean_control_effort=mean_effort, overshoot_count=overshoots,
+        max_overshoot=max_overshoot,
+        success=bool(duration >= criteria.min_episode_duration and ratio >= criteria.min_on_target_ratio),
+        termination_reason=info.get("termination_reason", ""), action_violations=info.get("action_violations", 0))
+
+
+def compute_evaluation_summary(episode_metrics_list, criteria: SuccessCriteria | None = None) -> EvaluationSummary:
+    """utils/metrics.py:341-390 for a list of EpisodeMetrics."""
+    criteria = criteria or SuccessCriteria()
+    if not episode_metrics_list:
+        return EvaluationSummary()
+    n = len(episode_metrics_list)
+    ratios = [m.on_target_ratio for m in episode_metrics_list]
+    errors = [m.mean_tracking_error for m in episode_metrics_list]
+    efforts = [m.mean_control_effort for m in episode_metrics_list]
+    successes = sum(1 for m in episode_metrics_list if m.success)
+    mean_ratio = float(np.mean(ratios))
+    return EvaluationSummary(
+        total_episodes=n, successful_episodes=successes, success_rate=successes / n, mean_on_target_ratio=mean_ratio,
+        std_on_target_ratio=float(np.std(ratios)), mean_tracking_error=float(np.mean(errors)),
+        std_tracking_error=float(np.std(errors)), mean_control_effort=float(np.mean(efforts)),
+        best_episode_idx=int(np.argmax(ratios)), worst_episode_idx=int(np.argmin(ratios)),
+        meets_criteria=mean_ratio >= criteria.min_on_target_ratio, episode_metrics=episode_metrics_list)
+
+
 def format_metrics_report(summary: EvaluationSummary) -> str:
     """Plain-text report in the spirit of utils/metrics.py:393-433."""
     em = summary.episode_metrics

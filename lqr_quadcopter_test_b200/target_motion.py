@@ -160,7 +160,8 @@ class TargetMotion:
         ctx = _lib.get_context()
         ctx.bind_torch_stream()
         f64 = dict(dtype=torch.float64, device=ctx.device)
-        seeds = torch.tensor([self._seed], dtype=torch.int64, device=ctx.device)
+        # the kernel reads the seed as an unsigned 64-bit integer: keep the bits of seeds above 2^63
+        seeds = torch.from_numpy(np.array([self._seed], dtype=np.uint64).view(np.int64)).to(ctx.device)
         # row 0: the env's own stream (unused here), row 1: the target's stream
         draws = torch.tensor([[0], [self._draws]], dtype=torch.int64, device=ctx.device)
         state, tp = torch.empty((12, 1), **f64), torch.empty((12, 1), **f64)
