@@ -25,6 +25,12 @@ constexpr int kRolloutThreads = 128;
 #ifndef QT_OPT_KREG
 #define QT_OPT_KREG 1
 #endif
+#ifndef QT_OPT_COLDPTR
+#define QT_OPT_COLDPTR 1
+#endif
+#ifndef QT_OPT_FINITE
+#define QT_OPT_FINITE 1   // structured loop: no per-step non-finite tests (proved impossible once per episode)
+#endif
 #ifndef QT_ROLLOUT_MIN_BLOCKS
 #define QT_ROLLOUT_MIN_BLOCKS 4  // resident blocks per SM the register allocator must allow (128 registers)
 #endif
@@ -72,6 +78,13 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
     const int64_t E = A.E;
     const int64_t chain_id = (int64_t)blockIdx.x * T + threadIdx.x;
     double *cold = smem + threadIdx.x;   // this thread's column of the cold tile: cold[row * T]
+#if QT_OPT_COLDPTR
+    // Keep that address in a register.  Left to itself ptxas rebuilds it from S2R TID.X / S2UR CgaCtaId / ULEA / LEA
+    // three times per env step (ncu r02_a: those 15 instructions carry the largest stall counts of the loop — they wait
+    // on the special-register reads); the empty asm hides where the value came from, the assumption keeps LDS / STS.
+    asm volatile("" : "+l"(cold));
+    __builtin_assume(__isShared(cold));
+#endif
     double *sK = smem + kColdRows * T;   // staged gains follow the tile (compile-time offset)
 
     int64_t g0 = 0;
@@ -169,7 +182,16 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             for (int i = 0; i < TargetParamCount<MOTION>::value; i++) hmax = max(hmax, hi_abs(cold[(CR_TARGET + i) * T]));
 #pragma unroll
             for (int i = 0; i < 3; i++) hmax = max(hmax, hi_abs(integ[i]));
-            fast = fast && hmax < 0x7ff00000;  // 0 * inf would differ from the dense products
+            // every gain entry as well: with a finite state, target, gain and constants the action is finite (it is a
+            // clamped affine function of them), the env never has to repair it, and the state stays finite for the
+            // whole episode — the structured loop drops both per-step non-finite tests (QT_OPT_FINITE)
+#pragma unroll
+            for (int i = 0; i < 4 * KC; i++) hmax = max(hmax, hi_abs(Kp[i]));
+            if (ffg) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) hmax = max(hmax, hi_abs(ffg[i]));
+            }
+            fast = fast && hmax < 0x7ff00000 && C.all_finite;  // (0 * inf would also differ from the dense products)
             if constexpr (CTRL != CK_PID) fast = fast && gain_is_axis_decoupled<CTRL == CK_LQI>(Kp);
         }
         const bool warp_fast = __all_sync(__activemask(), fast);
@@ -276,7 +298,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 
             // ---- env.step (quadcopter_env.py:171-207)
             double actv[4], eta_old[3];
-            violations += A.env_bounds_check ? validate_action<true>(P, act, actv) : validate_action<false>(P, act, actv);
+            if constexpr (FAST && QT_OPT_FINITE)
+                violations += A.env_bounds_check ? validate_action<true, false>(P, act, actv) : validate_action<false, false>(P, act, actv);
+            else
+                violations += A.env_bounds_check ? validate_action<true>(P, act, actv) : validate_action<false>(P, act, actv);
             if (euler)
                 integrate<true, FAST>(C, s, actv, B, eta_old);
             else if (QT_OPT_FLAT_RK4)
@@ -297,7 +322,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 sqrt_pair(dx * dx + dy * dy + dz * dz, effort2, err_post, effort);
                 cold[CR_SUM_EFF * T] += effort;
             }
-            term = termination_code(P, C, s, t);
+            term = termination_code<FAST && QT_OPT_FINITE>(P, C, s, t);
             env_on += (err_post <= P.env_target_radius) ? 1 : 0;
             if constexpr (FULL) {
                 if (log_traj) {
