@@ -28,6 +28,9 @@ constexpr int kRolloutThreads = 128;
 #ifndef QT_OPT_COLDPTR
 #define QT_OPT_COLDPTR 1
 #endif
+#ifndef QT_OPT_RARE
+#define QT_OPT_RARE 3     // one combined test + branch for the step's rare range events (1: all, 2: tilt separate, 3: 1 for LQR / PID, 2 for LQI)
+#endif
 #ifndef QT_OPT_FINITE
 #define QT_OPT_FINITE 1   // structured loop: no per-step non-finite tests (proved impossible once per episode)
 #endif
@@ -308,7 +311,27 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 integrate_flat<FAST>(C, s, actv, B, eta_old);
             else
                 integrate<false, FAST>(C, s, actv, B, eta_old);
+#if QT_OPT_RARE
+            // one branch for the step's rare range events instead of four (body rates, speed, position bound and —
+            // except for the LQI law, whose default gains sit in the tilt limit most of the time — tilt / wrap); the
+            // usual step only takes the wrap's roundings (a + pi) - pi
+            constexpr bool kTiltFused = (QT_OPT_RARE == 1) || (QT_OPT_RARE == 3 && CTRL != CK_LQI);
+            const bool unusual = step_is_unusual<FAST, kTiltFused>(C, s, s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
+            if (!unusual) {
+                if constexpr (kTiltFused) {
+                    s[6] = (s[6] + kPi) - kPi;
+                    s[7] = (s[7] + kPi) - kPi;
+                    if (!FAST) s[8] = (s[8] + kPi) - kPi;
+                } else {
+                    constrain_attitude<FAST>(s);
+                }
+            } else {
+                constrain_state<FAST>(P, C, s);
+            }
+#else
+            constexpr bool unusual = true;
             constrain_state<FAST>(P, C, s);
+#endif
             trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
             {
                 const double t_old = t;
@@ -322,7 +345,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                 sqrt_pair(dx * dx + dy * dy + dz * dz, effort2, err_post, effort);
                 cold[CR_SUM_EFF * T] += effort;
             }
-            term = termination_code<FAST && QT_OPT_FINITE>(P, C, s, t);
+            if (t >= P.max_episode_time)
+                term = QT_TERM_TIME_LIMIT;
+            else if (unusual || !(FAST && QT_OPT_FINITE))
+                term = termination_code<FAST && QT_OPT_FINITE>(P, C, s, t);
             env_on += (err_post <= P.env_target_radius) ? 1 : 0;
             if constexpr (FULL) {
                 if (log_traj) {
