@@ -28,6 +28,9 @@ constexpr int kRolloutThreads = 128;
 #ifndef QT_OPT_COLDPTR
 #define QT_OPT_COLDPTR 1
 #endif
+#ifndef QT_OPT_DATASTAGE
+#define QT_OPT_DATASTAGE 1   // teacher data set: feature rows leave through a per-warp shared-memory tile, fully coalesced
+#endif
 #ifndef QT_OPT_RARE
 #define QT_OPT_RARE 3     // one combined test + branch for the step's rare range events (1: all, 2: tilt separate, 3: 1 for LQR / PID, 2 for LQI)
 #endif
@@ -278,8 +281,6 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             if constexpr (DATA) {
                 if (A.feat && step == next_data && data_slot < A.data_slots) {
                     // deep_tracking_policy.py:241-286 feature layout, fp32
-                    float2 *f = reinterpret_cast<float2 *>(A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM);
-                    float2 *y = reinterpret_cast<float2 *>(A.actf + ((int64_t)data_slot * E + e) * QT_ACTION_DIM);
                     float ft[18];
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
@@ -290,10 +291,51 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                         ft[12 + i] = (float)tp[i];
                         ft[15 + i] = (float)tv[i];
                     }
+                    const int64_t row = (int64_t)data_slot * E + e;
+                    float *yrow = A.actf + row * QT_ACTION_DIM;
+                    float *frow = A.feat + row * QT_FEATURE_DIM;
+#if QT_OPT_DATASTAGE
+                    // Coalesced rows.  An action row is 16 bytes: one float4 per lane, 512 contiguous bytes per warp.
+                    // A feature row is 72 bytes; written per thread, a warp's store touches 32 different sectors per
+                    // instruction (ncu r02_a: 8.8 useful bytes per 32-byte sector).  When all 32 lanes of the warp log
+                    // the same slot — always, until episodes of the warp end at different steps — the rows are laid
+                    // side by side in a per-warp shared-memory tile and leave as 144 float4 = 2304 contiguous bytes.
+                    const int lane = threadIdx.x & 31;
+                    const int64_t row0 = row - lane;                     // the warp's first row
+                    const bool aligned16 = ((reinterpret_cast<uintptr_t>(A.feat) | reinterpret_cast<uintptr_t>(A.actf)) & 15) == 0;
+                    if (aligned16) {
+                        *reinterpret_cast<float4 *>(yrow) = make_float4((float)act[0], (float)act[1], (float)act[2], (float)act[3]);
+                    } else {
+                        reinterpret_cast<float2 *>(yrow)[0] = make_float2((float)act[0], (float)act[1]);
+                        reinterpret_cast<float2 *>(yrow)[1] = make_float2((float)act[2], (float)act[3]);
+                    }
+                    if (__activemask() == 0xffffffffu && aligned16 && (row0 & 1) == 0) {
+                        float *tile = reinterpret_cast<float *>(smem + kColdRows * T + A.k_smem_doubles) + (threadIdx.x >> 5) * (32 * QT_FEATURE_DIM);
+                        float2 *mine = reinterpret_cast<float2 *>(tile + lane * QT_FEATURE_DIM);
+#pragma unroll
+                        for (int i = 0; i < 9; i++) mine[i] = make_float2(ft[2 * i], ft[2 * i + 1]);
+                        __syncwarp();
+                        const float4 *src = reinterpret_cast<const float4 *>(tile);
+                        float4 *dst = reinterpret_cast<float4 *>(A.feat + row0 * QT_FEATURE_DIM);
+#pragma unroll
+                        for (int k = 0; k < 5; k++) {
+                            const int idx = lane + 32 * k;
+                            if (idx < 32 * QT_FEATURE_DIM / 4) dst[idx] = src[idx];
+                        }
+                        __syncwarp();
+                    } else {
+                        float2 *f = reinterpret_cast<float2 *>(frow);
+#pragma unroll
+                        for (int i = 0; i < 9; i++) f[i] = make_float2(ft[2 * i], ft[2 * i + 1]);
+                    }
+#else
+                    float2 *f = reinterpret_cast<float2 *>(frow);
+                    float2 *y = reinterpret_cast<float2 *>(yrow);
 #pragma unroll
                     for (int i = 0; i < 9; i++) f[i] = make_float2(ft[2 * i], ft[2 * i + 1]);
                     y[0] = make_float2((float)act[0], (float)act[1]);
                     y[1] = make_float2((float)act[2], (float)act[3]);
+#endif
                     next_data += A.data_stride;
                     data_slot += 1;
                 }
@@ -301,6 +343,10 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
 
             // ---- env.step (quadcopter_env.py:171-207)
             double actv[4], eta_old[3];
+            // re-basing of the carried attitude trig inside the integrator's stage block (RK4 only)
+            constexpr bool kRebaseInline = QT_OPT_REBASE4 && QT_OPT_STAGES3 && QT_OPT_FOLDED_RK4 && QT_OPT_FLAT_RK4 && QT_OPT_RARE;
+            [[maybe_unused]] Trig Bnext;
+            [[maybe_unused]] bool attitude_changed = false;
             if constexpr (FAST && QT_OPT_FINITE)
                 violations += A.env_bounds_check ? validate_action<true, false>(P, act, actv) : validate_action<false, false>(P, act, actv);
             else
@@ -308,7 +354,7 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             if (euler)
                 integrate<true, FAST>(C, s, actv, B, eta_old);
             else if (QT_OPT_FLAT_RK4)
-                integrate_flat<FAST>(C, s, actv, B, eta_old);
+                integrate_flat<FAST>(C, s, actv, B, eta_old, kRebaseInline ? &Bnext : nullptr);
             else
                 integrate<false, FAST>(C, s, actv, B, eta_old);
 #if QT_OPT_RARE
@@ -323,16 +369,26 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
                     s[7] = (s[7] + kPi) - kPi;
                     if (!FAST) s[8] = (s[8] + kPi) - kPi;
                 } else {
-                    constrain_attitude<FAST>(s);
+                    attitude_changed = constrain_attitude<FAST>(s);
                 }
             } else {
+                attitude_changed = true;
                 constrain_state<FAST>(P, C, s);
             }
 #else
             constexpr bool unusual = true;
             constrain_state<FAST>(P, C, s);
 #endif
-            trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
+            if (kRebaseInline && !euler) {
+                // Bnext belongs to the attitude the integrator produced; the constraints usually only re-round it
+                // ((a + pi) - pi, <= 2.3e-16).  A wrap, a clip or the periodic re-synchronisation evaluates directly.
+                if (attitude_changed || (step & 15) == 15)
+                    trig_rebase<FAST>(eta_old, s, true, B);
+                else
+                    B = Bnext;
+            } else {
+                trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
+            }
             {
                 const double t_old = t;
                 t += C.dt;
@@ -504,7 +560,8 @@ static int rollout_launch(qt_context *ctx, const qt_params *params, qt::RolloutA
         }
     }
     // the per-thread cold-state tile (kColdRows x 128 doubles = 17 KB) + staged gains
-    const size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
+    size_t smem = ((size_t)A.k_smem_doubles + (size_t)kColdRows * kRolloutThreads) * sizeof(double);
+    if (A.feat) smem += (size_t)(kRolloutThreads / 32) * 32 * QT_FEATURE_DIM * sizeof(float);   // data-set staging tiles
     const bool needs_full = params->feedforward_enabled || params->integrator != QT_INTEGRATOR_RK4 || A.traj != nullptr;
     const int full = needs_full ? 1 : (A.feat != nullptr ? 2 : 0);   // kernel MODE
 
