@@ -78,7 +78,11 @@ def workload_config(n_gpus: int, episodes: int) -> dict:
 
 # ----------------------------------------------------------------------------- clock sampling --
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in the background, one line every 20 ms.  It is started BEFORE the warm-up (nvidia-smi needs a few
+    hundred ms to come up, longer when eight ranks start theirs at once) and the samples of the timed region are picked
+    by their timestamps: mark() right before and right after the region."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -86,6 +90,7 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
@@ -93,14 +98,21 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
         return self
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def __exit__(self, *exc):
         if self.proc is not None:
+            time.sleep(0.05)      # let the last samples of the region reach the file
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -108,31 +120,41 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm, sm_max, power, reasons = [], [], [], set()
+        import datetime
+
+        rows = []
         try:
             for line in open(self.path):
                 parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 7:
+                if len(parts) < 8:
                     continue
                 try:
-                    sm.append(float(parts[0]))
-                    sm_max.append(float(parts[1]))
-                    power.append(float(parts[2]))
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     parts[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
         except OSError:
             pass
         finally:
             if self.path and os.path.exists(self.path):
                 os.unlink(self.path)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(sm_max), "power_w_max": max(power),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t0, t1 = self.t0 or rows[0][0], self.t1 or rows[-1][0]
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        note = "samples inside the timed region"
+        if len(inside) < 3:           # a very short region: the samples closest to it (the GPU is under the same load
+            mid = 0.5 * (t0 + t1)     # during the warm-up passes right before)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:5]
+            note = "timed region shorter than the sampling period: the five samples closest to it"
+        reasons = set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                "power_w_max": max(r[3] for r in inside), "reasons": sorted(reasons), "samples": len(inside),
+                "sampling": f"nvidia-smi -lms 20, {note}"}
 
 
 # ------------------------------------------------------------------------------ CPU baseline --
@@ -513,17 +535,19 @@ def run_gpu_arm(args) -> None:
             kernel_events.append((ev0, ev1))
 
     kernel_events: list = []
-    for _ in range(args.warmup):
-        one_pass(False)
-    barrier()
-    launches0 = ctx.launches
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            one_pass(False)
+        barrier()
+        launches0 = ctx.launches
+        clocks.mark_start()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):
             one_pass(True)
         t1.record()
         barrier()
+        clocks.mark_end()
         elapsed_ms = t0.elapsed_time(t1)
     gpu_launches = ctx.launches - launches0
     clock_info = clocks.summary()

@@ -11,10 +11,16 @@ experiment logs.  What changes is where the work happens:
 * updates — one optimiser step per episode on ``batch_size`` random steps of that episode, exactly
   the reference's schedule (train.py:751-862), evaluated by torch autograd on those tensors.
 
-Deliberate difference: the reference updates the network between the episodes of an epoch, so episode
-i+1 is driven by the weights after episode i; here the episodes of one epoch are driven by the weights
-the epoch started with (they run concurrently).  The staleness is below one epoch and vanishes for
-``episodes_per_epoch = 1``.
+Two update schedules (``Trainer(config, update_schedule=...)``):
+
+* ``"epoch"`` (default, the fast one): the episodes of one epoch are driven by the weights the epoch started with —
+  they run concurrently in one launch — and the per-episode optimiser steps follow.  The reference updates the
+  network BETWEEN the episodes of an epoch (train.py:660-735), so its episode i+1 is driven by the weights after
+  episode i; the staleness here is below one epoch and vanishes for ``episodes_per_epoch = 1``.
+* ``"episode"`` (exact): one launch per episode, the optimiser step right after it, batches drawn with
+  ``np.random.choice`` from numpy's global generator — the reference's order of operations, step for step.  This is
+  the mode ``tests/test_train_gpu.py`` holds to a loss curve recorded from the reference's own trainer
+  (``tests/golden/trainer.npz``, ``oracle/gen_golden.py::gen_trainer``).
 """
 from __future__ import annotations
 
@@ -107,10 +113,21 @@ class LossLogger:
 
     def log(self, losses: dict) -> None:
         for k, v in losses.items():
-            self.current.setdefault(k, []).append(float(v))
+            self.current.setdefault(k, []).append(v)       # device tensors stay on the device until the epoch ends
 
     def end_epoch(self) -> dict[str, float]:
-        out = {k: float(np.mean(v)) for k, v in self.current.items() if v}
+        out = {}
+        for k, vals in self.current.items():
+            if not vals:
+                continue
+            if any(hasattr(v, "detach") for v in vals):     # one read-back per component and epoch, not one per step
+                import torch
+
+                host = torch.stack([torch.as_tensor(v, dtype=torch.float64, device=vals[0].device) if not hasattr(v, "detach")
+                                    else v.detach().to(torch.float64) for v in vals]).cpu().numpy()
+                out[k] = float(np.mean(host))
+            else:
+                out[k] = float(np.mean(vals))
         self.history.append(out)
         self.current = {}
         return out
@@ -138,9 +155,12 @@ def _weighted_error(torch, err, weight: float, kind: str, delta: float = 1.0):
 class Trainer:
     """train.py:275-1028."""
 
-    def __init__(self, config: TrainingConfig):
+    def __init__(self, config: TrainingConfig, update_schedule: str = "epoch"):
         import torch
 
+        if update_schedule not in ("epoch", "episode"):
+            raise ValueError(f"update_schedule must be 'epoch' or 'episode', got {update_schedule!r}")
+        self.update_schedule = update_schedule
         self.config = config
         self.full_config = getattr(config, "full_config", {})
         self._ctx = _lib.get_context()           # raises without a GPU: there is no CPU training path
@@ -249,6 +269,8 @@ class Trainer:
         import torch
 
         c = self.config
+        if self.update_schedule == "episode":
+            return self._train_epoch_exact(difficulty)
         out = rollout_device(self.controller, self.env_config, self.criteria, self._epoch_seeds(),
                              c.max_steps_per_episode, dataset_stride=1, ctx=self._ctx, supervisor=self.supervisor)
         feats, labels = out["features"], out["actions"]          # [slots, E, 18], [slots, E, 4]
@@ -262,7 +284,29 @@ class Trainer:
             self._update_from_episode(feats[:n, ep], labels[:n, ep] if self.supervisor is not None else None)
         return {**self._episode_stats(out, first_err), "difficulty": difficulty}
 
-    def _update_from_episode(self, features, supervisor_actions) -> None:
+    def _train_epoch_exact(self, difficulty: float = 1.0) -> dict:
+        """train.py:654-749 in the reference's own order: episode, optimiser step, next episode with the new weights."""
+        import torch
+
+        c = self.config
+        seeds = self._epoch_seeds()
+        stats = []
+        for ep in range(c.episodes_per_epoch):
+            out = rollout_device(self.controller, self.env_config, self.criteria, seeds[ep:ep + 1].contiguous(),
+                                 c.max_steps_per_episode, dataset_stride=1, ctx=self._ctx, supervisor=self.supervisor)
+            n = int(out["metrics"][P.M_STEPS, 0].item())
+            if n <= 0:
+                continue
+            feats, labels = out["features"], out["actions"]
+            first_err = feats[0, :, 0:3].to(torch.float64).norm(dim=1)
+            stats.append(self._episode_stats(out, first_err))
+            self._step_counter += 1
+            self._update_from_episode(feats[:n, 0], labels[:n, 0] if self.supervisor is not None else None,
+                                      numpy_batches=True)
+        keys = ("mean_reward", "mean_on_target_ratio", "mean_tracking_error")
+        return {**{k: float(np.mean([s[k] for s in stats])) if stats else 0.0 for k in keys}, "difficulty": difficulty}
+
+    def _update_from_episode(self, features, supervisor_actions, numpy_batches: bool = False) -> None:
         """train.py:751-862: one optimiser step on ``batch_size`` random steps of one episode."""
         import torch
         import torch.nn.functional as F
@@ -270,7 +314,10 @@ class Trainer:
         c = self.config
         n = int(features.shape[0])
         batch = min(c.batch_size, n)
-        idx = torch.randperm(n, device=self.device, generator=self._gen)[:batch]
+        if numpy_batches:   # the reference's draw: numpy's global generator, without replacement (train.py:757)
+            idx = torch.as_tensor(np.random.choice(n, batch, replace=False), device=self.device)
+        else:
+            idx = torch.randperm(n, device=self.device, generator=self._gen)[:batch]
         x = features[idx]
         actions = self.controller.network(x)
         pos_error, vel_error = x[:, 0:3], x[:, 3:6]

@@ -675,11 +675,48 @@ def gen_policy():
     np.savez_compressed(OUT / "policy.npz", **out)
 
 
+TRAINER_CASE = dict(controller="deep", epochs=3, episodes_per_epoch=3, max_steps_per_episode=80, batch_size=16,
+                    learning_rate=0.002, hidden_sizes=[32, 32], activation="tanh", training_mode="imitation",
+                    supervisor_controller="riccati_lqr", imitation_weight=1.0, tracking_weight=0.05, env_seed=123,
+                    target_motion_type="circular", episode_length=30.0, device="cpu", checkpoint_interval=1000,
+                    save_best=False)
+
+
+def gen_trainer():
+    """§8(f).2: the reference's imitation trainer (train.py:654-862) on a small run — three epochs of three episodes,
+    one optimiser step after EVERY episode on batch_size steps drawn with the global numpy generator — recorded as
+    initial weights, per-epoch loss components / rollout statistics and final weights.  The drop-in's trainer in its
+    exact update order (Trainer(update_schedule="episode")) is held to this curve in tests/test_train_gpu.py."""
+    import torch
+
+    from quadcopter_tracking.train import Trainer, TrainingConfig
+
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.manual_seed(0)
+        np.random.seed(0)
+        cfg = TrainingConfig(**TRAINER_CASE, checkpoint_dir=os.path.join(tmp, "ck"), log_dir=os.path.join(tmp, "logs"))
+        tr = Trainer(cfg)
+        lin = [m for m in tr.controller.network.modules() if isinstance(m, torch.nn.Linear)]
+        for i, l in enumerate(lin):
+            out[f"W0_{i}"] = l.weight.detach().numpy().copy()
+            out[f"b0_{i}"] = l.bias.detach().numpy().copy()
+        tr.train()
+        keys = ("total", "imitation", "tracking_total", "mean_reward", "mean_on_target_ratio", "mean_tracking_error")
+        for k in keys:
+            out[k] = np.array([e[k] for e in tr.experiment_log], dtype=np.float64)
+        for i, l in enumerate(lin):
+            out[f"W1_{i}"] = l.weight.detach().numpy().copy()
+            out[f"b1_{i}"] = l.bias.detach().numpy().copy()
+    np.savez_compressed(OUT / "trainer.npz", **out)
+    print("trainer.npz", {k: out[k] for k in ("total", "imitation", "mean_tracking_error")})
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     _import_reference()
     cwd = os.getcwd()
-    every = (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts, gen_pid_lqr, gen_policy)
+    every = (gen_reset, gen_dare, gen_step_edges, gen_controller, gen_eval_summary, gen_tuning, gen_rollouts, gen_pid_lqr, gen_policy, gen_trainer)
     chosen = [fn for fn in every if fn.__name__ in sys.argv[1:]] or every   # e.g. `gen_golden.py gen_pid_lqr`
     for fn in chosen:
         print(fn.__name__, flush=True)
