@@ -31,6 +31,9 @@ namespace qt {
 #define QT_DARE_N9 9     // n = 7..9 (LQI): 3 lanes x 3 rows, 10 systems per warp
 #define QT_DARE_R9 3
 #endif
+#ifndef QT_DARE_BLOCKSYNC
+#define QT_DARE_BLOCKSYNC 20  // kernels with R * N >= this value keep the warps of a block in step (see dare_kernel): n = 9 +6 %, n = 12 +3 %, n = 6 -4 % (A/B r02_o)
+#endif
 #ifndef QT_DARE_R6
 #define QT_DARE_R6 3     // n = 5, 6: 2 lanes x 3 rows, 16 systems per warp
 #endif
@@ -403,6 +406,15 @@ __global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_
     bool conv = false;
     int iters = 0;
     for (int it = 0; it < kDareMaxIter; it++) {
+#if QT_DARE_BLOCKSYNC
+        // The warps of a block walk the doubling body together: it is tens of KB of straight-line SASS (fully unrolled
+        // register-array code), and warps at different places in it evict each other's instruction-cache lines (ncu
+        // r02 n = 9: 40 % of the stall samples were instruction fetches).  The block leaves the loop when all of its
+        // systems have converged; converged systems keep H frozen, so the extra doublings change nothing.
+        if (DareCfg<N, R>::RN >= QT_DARE_BLOCKSYNC) {
+            if (__syncthreads_and(conv || ghost)) break;
+        } else
+#endif
         if (__all_sync(0xffffffffu, conv || ghost)) break;
         __syncwarp();  // the rows of A_k / H_k stored by the team are visible
         {
