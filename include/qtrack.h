@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define QT_ABI_VERSION 5
+#define QT_ABI_VERSION 6
 
 #define QT_STATE_DIM 12     /* env/quadcopter_env.py:63-70  [p(3) v(3) roll,pitch,yaw  p,q,r] */
 #define QT_ACTION_DIM 4     /* thrust, roll_rate, pitch_rate, yaw_rate (controllers/base.py:28) */
@@ -170,6 +170,14 @@ void *qt_get_stream(const qt_context *ctx);
 int qt_synchronize(qt_context *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t qt_launch_count(const qt_context *ctx);
+/* Which kernels qt_dare_batched (and the host / sweep calls built on it) may use (ABI v6).  QT_DARE_PATH_AUTO:
+   systems that are block diagonal after a permutation of the states, with blocks of at most three states and one
+   control, diagonal Q and R — every design of riccati_lqr.py:187-316, 602-700 — are solved block by block in
+   registers; all others by the dense kernel.  QT_DARE_PATH_DENSE: the dense kernel for every system (tests and
+   measurements).  Both paths return the same solution. */
+#define QT_DARE_PATH_AUTO 0
+#define QT_DARE_PATH_DENSE 1
+int qt_set_dare_path(qt_context *ctx, int32_t path);
 
 /* ---- A1: QuadcopterEnv.reset(seed) + TargetMotion.reset/_create_pattern ------------------
  * quadcopter_env.py:111-150, target_motion.py:291-369.  One seed per episode; reproduces

@@ -25,6 +25,7 @@ ABI_SYMBOLS = (
     "qt_reduce_scores", "qt_reduce_summary", "qt_evaluate_host", "qt_fp64_peak_probe",
     "qt_mlp_packed_floats", "qt_policy_action_batched", "qt_rollout_policy", "qt_sqrt_pair_probe",
     "qt_fill_seeds", "qt_rollout_sweep", "qt_dare_host", "qt_sweep_host", "qt_fp32_peak_probe",
+    "qt_set_dare_path",
 )
 
 _lib = None
@@ -60,6 +61,7 @@ def load_library() -> C.CDLL:
             "qt_get_stream": (vp, [vp]),
             "qt_synchronize": (C.c_int, [vp]),
             "qt_launch_count": (i64, [vp]),
+            "qt_set_dare_path": (C.c_int, [vp, i32]),
             "qt_reset_batched": (C.c_int, [vp, PP, vp, i64, vp, vp, vp]),
             "qt_rng_probe": (C.c_int, [vp, vp, i64, i32, i32, vp]),
             "qt_observe_batched": (C.c_int, [vp, PP, i64, vp, vp, vp, vp]),
@@ -216,6 +218,10 @@ class Context:
         self.check(self.lib.qt_sweep_host(self.handle, C.byref(params), n, C_, eps, int(seed0) & (2 ** 64 - 1), max_steps,
                                           _ptr(q_host), _ptr(r_host), float(ctrl_mass), float(ctrl_gravity),
                                           _ptr(cand_out_host), _ptr(K_out_host), _ptr(info_out_host)))
+
+    def set_dare_path(self, path: int) -> None:
+        """0 = automatic (decoupled blocks in registers where the system allows it), 1 = dense kernel only."""
+        self.check(self.lib.qt_set_dare_path(self.handle, int(path)))
 
     def dare_batched(self, n, m, batch, A, strideA, B, strideB, Q, strideQ, R, strideR, P_out,
                      K_out, iters_out, info_out):

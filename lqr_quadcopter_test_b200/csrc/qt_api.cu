@@ -119,6 +119,13 @@ extern "C" void qt_destroy(qt_context *ctx) {
     delete ctx;
 }
 
+extern "C" int qt_set_dare_path(qt_context *ctx, int32_t path) {
+    if (!ctx) return QT_ERR_ARG;
+    QT_REQUIRE(ctx, path == QT_DARE_PATH_AUTO || path == QT_DARE_PATH_DENSE, "unknown DARE path");
+    ctx->dare_path = path;
+    return QT_OK;
+}
+
 extern "C" const char *qt_last_error(const qt_context *ctx) { return ctx ? ctx->err : "null context"; }
 
 extern "C" int qt_set_stream(qt_context *ctx, void *cuda_stream) {

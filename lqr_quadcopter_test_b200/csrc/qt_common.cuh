@@ -15,6 +15,7 @@ struct qt_context {
     cudaStream_t aux_stream;  // second lane of the host-buffer entry points' copy/compute pipeline
     cudaEvent_t ev_inputs, ev_aux_done;  // ordering between the two lanes (timing disabled)
     int sm_count;
+    int dare_path;            // QT_DARE_PATH_* (qt_set_dare_path)
     int64_t launches;
     // scratch owned by the library (host-buffer entry points only; never handed to the caller)
     void *scratch_dev;

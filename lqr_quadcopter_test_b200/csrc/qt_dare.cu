@@ -23,6 +23,7 @@
 // is branch free).  n and m are zero-padded to the next instantiated N, which leaves the solution of the original
 // system unchanged (block-diagonal embedding).
 #include "qt_common.cuh"
+#include "qt_dare_blocks.cuh"
 
 namespace qt {
 
@@ -350,7 +351,10 @@ __global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_
     const int64_t sys = ((int64_t)blockIdx.x * WARPS + warp) * L::TEAMS + team;
     const int n = D.n, m = D.m;
     bool ghost = (team >= L::TEAMS) || (sys >= D.batch);
-    if (!ghost && D.info[sys] == 3) ghost = true;  // rejected by the validation kernel
+    // only systems the validation kernel passed on: rejected ones (info = 3) and the ones the decoupled path has
+    // already solved (qt_dare_blocks.cuh) are skipped
+    if (!ghost && D.info[sys] != kDareMarkValid) ghost = true;
+    if (__syncthreads_and(ghost)) return;  // nothing for this block to do (the usual case after the decoupled path)
 
     // Shared memory of one team: four N x N matrices and the pivot-row buffer.  pA holds A_k, pY receives
     // Y = W^-1 G_k and then A_{k+1} (the two pointers are exchanged at the end of a doubling), sH holds H_k,
@@ -631,9 +635,12 @@ __device__ bool allclose_sym(const double *M, int n) {
     return true;
 }
 
-__global__ void dare_validate_kernel(const __grid_constant__ DareArgs D) {
+// only_marked: the decoupled path ran first and left the systems it did not take with info = kDareMarkDense.
+// Accepted systems are handed to the dense kernel with info = kDareMarkValid.
+__global__ void dare_validate_kernel(const __grid_constant__ DareArgs D, int only_marked) {
     const int64_t sys = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= D.batch) return;
+    if (only_marked && D.info[sys] != kDareMarkDense) return;
     // shared Q / R (stride 0) need to be checked only once, but the check is cheap: keep it simple
     const double *Q = D.Q + sys * D.sQ, *R = D.R + sys * D.sR;
     bool ok = allclose_sym(Q, D.n) && allclose_sym(R, D.m);
@@ -642,7 +649,7 @@ __global__ void dare_validate_kernel(const __grid_constant__ DareArgs D) {
         const double rmin = min_eig_sym(R, D.m, D.m);
         ok = !(qmin < -1e-10) && (qmin == qmin) && (rmin > 1e-10);
     }
-    D.info[sys] = ok ? 0 : 3;
+    D.info[sys] = ok ? kDareMarkValid : 3;
     D.iters[sys] = 0;
 }
 
@@ -702,11 +709,28 @@ extern "C" int qt_dare_batched(qt_context *ctx, int32_t n, int32_t m, int64_t ba
     DareArgs D{n, m, batch, A_dev, B_dev, Q_dev, R_dev, strideA, strideB, strideQ, strideR,
                P_out_dev, K_out_dev, iters_out_dev, info_out_dev};
     DeviceGuard guard(ctx->device);
-    dare_validate_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(D);
-    int rc = check_launch(ctx, "dare_validate_kernel");
+    cudaError_t err;
+    int rc;
+    // decoupled path first (qt_dare_blocks.cuh): systems that are block diagonal with blocks of at most three states
+    // are solved there; the rest is marked and goes through validation + the dense kernel below
+    const bool try_blocks = ctx->dare_path != QT_DARE_PATH_DENSE && dare_blocks_applicable(n, m);
+    if (try_blocks) {
+        if (n <= 6)
+            err = launch_dare_blocks_n<6>(n, m, batch, A_dev, B_dev, Q_dev, R_dev, strideA, strideB, strideQ, strideR,
+                                          P_out_dev, K_out_dev, iters_out_dev, info_out_dev, kDareMaxIter, kDareTol, ctx->stream);
+        else if (n <= 9)
+            err = launch_dare_blocks_n<9>(n, m, batch, A_dev, B_dev, Q_dev, R_dev, strideA, strideB, strideQ, strideR,
+                                          P_out_dev, K_out_dev, iters_out_dev, info_out_dev, kDareMaxIter, kDareTol, ctx->stream);
+        else
+            err = launch_dare_blocks_n<12>(n, m, batch, A_dev, B_dev, Q_dev, R_dev, strideA, strideB, strideQ, strideR,
+                                           P_out_dev, K_out_dev, iters_out_dev, info_out_dev, kDareMaxIter, kDareTol, ctx->stream);
+        if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "dare_blocks_kernel launch", cudaGetErrorString(err));
+        ctx->launches += 1;
+    }
+    dare_validate_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(D, try_blocks ? 1 : 0);
+    rc = check_launch(ctx, "dare_validate_kernel");
     if (rc) return rc;
     const int need = n > m ? n : m;
-    cudaError_t err;
     // <padded size N, rows per lane R>: lanes per system N / R, systems per warp 32 / (N / R)
     if (need <= 4) err = launch_dare<4, 2>(D, ctx->stream);          // 2 lanes, 16 systems per warp
     else if (need <= 6) err = launch_dare<6, QT_DARE_R6>(D, ctx->stream);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_struct_layout_and_defaults():
     lib = _lib.load_library()
-    assert lib.qt_abi_version() == 5
+    assert lib.qt_abi_version() == 6
     assert lib.qt_params_size() == ctypes.sizeof(QtParams)
     p = QtParams()
     lib.qt_params_default(ctypes.byref(p))

@@ -1,6 +1,9 @@
 """DARE-only micro benchmark (device-resident matrices, CUDA events):
 
-    python tools/bench_dare.py [batch] [brief|full] [sizes, e.g. 6,9]
+    python tools/bench_dare.py [batch] [brief|full] [sizes, e.g. 6,9] [auto|dense]
+
+auto (default): qt_dare_batched as shipped — the reference's designs take the decoupled path (blocks in registers);
+dense: QT_DARE_PATH_DENSE, every system through the dense doubling kernel.
 
 n = 6 and n = 9: the reference's LQR / LQI designs on the tuning ranges (qt_build_lqr_systems);
 n = 12 and n = 15 (m = 4): the sizes the north star names — chains of integrators with random coupling, dense SPD Q,
@@ -37,6 +40,8 @@ if __name__ == "__main__":
     brief = len(sys.argv) > 2 and sys.argv[2] == "brief"
     sizes = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (6, 9, 12, 15)
     ctx = _lib.get_context()
+    path = sys.argv[4] if len(sys.argv) > 4 else "auto"
+    ctx.set_dare_path(1 if path == "dense" else 0)
     dev = ctx.device
     f64 = dict(dtype=torch.float64, device=dev)
     rng = np.random.default_rng(42)
@@ -68,7 +73,7 @@ if __name__ == "__main__":
         ms = e0.elapsed_time(e1) / reps
         k = iters.double().mean().item()
         if brief:
-            print(f"n={n}: {nb / ms * 1e3:.3e}/s", flush=True)
+            print(f"n={n} [{path}]: {nb / ms * 1e3:.3e}/s", flush=True)
         else:
-            print(f"n={n} batch={nb}: {ms:.3f} ms/launch  {nb / ms * 1e3:.4e} solves/s  {nb / ms * 1e3 * w_dare(n, 4, k) / 1e12:.2f} TFLOP/s  "
+            print(f"n={n} [{path}] batch={nb}: {ms:.4f} ms/launch  {nb / ms * 1e3:.4e} solves/s  {nb / ms * 1e3 * w_dare(n, 4, k) / 1e12:.2f} TFLOP/s  "
                   f"iters mean {k:.2f} max {iters.max().item()}  failed {(info != 0).sum().item()}", flush=True)
