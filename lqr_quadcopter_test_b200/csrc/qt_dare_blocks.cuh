@@ -37,6 +37,15 @@ constexpr int kDareMarkDense = -1;  // info: left to the dense path (not yet val
 constexpr int kDareMarkValid = -2;  // info: validated, to be solved by the dense kernel
 constexpr int kBlkMaxS = 3;         // largest block the register solver is instantiated for
 constexpr int kBlkMaxTile = 192;    // doubles of P + K per system the per-warp output tile may hold (32 x 192 x 8 = 48 KB)
+// Registers per thread (A/B on one B200, profiles/r02_dare_blocks_ab.txt).  The 3 x 3 block solver needs ~166 for a
+// spill-free doubling loop (12 warps per SM); systems of up to six states mostly decompose into 2 x 2 blocks, whose
+// solver is small, and gain more from 16 resident warps (128 registers; only the 3 x 3 instance spills there).
+#ifndef QT_BLK_MAXREG
+#define QT_BLK_MAXREG 168
+#endif
+#ifndef QT_BLK_MAXREG6
+#define QT_BLK_MAXREG6 128
+#endif
 
 struct DareArgs;  // qt_dare.cu
 
@@ -255,7 +264,7 @@ __device__ __forceinline__ void blk_solve(const double *Ap, const double *Bp, co
 
 // NMAX: compile-time bound of n for the unrolled structure detection (6, 9 or 12).
 template <int NMAX>
-__global__ void __launch_bounds__(32, 12)
+__global__ void __maxnreg__(NMAX <= 6 ? QT_BLK_MAXREG6 : QT_BLK_MAXREG)
     dare_blocks_kernel(int n, int m, int64_t batch, const double *__restrict__ A, const double *__restrict__ B,
                        const double *__restrict__ Q, const double *__restrict__ R, int64_t sA, int64_t sB, int64_t sQ,
                        int64_t sR, double *__restrict__ P_out, double *__restrict__ K_out, int32_t *__restrict__ iters_out,

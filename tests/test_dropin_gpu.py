@@ -192,8 +192,9 @@ def test_cma_es_strategy_runs_generations_as_batches_and_improves(gpu_ctx, tmp_p
     launches0 = gpu_ctx.launches
     res = tuner.tune()
     assert res.iterations_completed == 120 and len(res.all_results) == 120
-    # 10 generations; each is reset + build + validate + DARE + rollout + reduce, not 12 separate evaluations
-    assert gpu_ctx.launches - launches0 <= 10 * 8
+    # 10 generations; each is seeds + reset + build + DARE (decoupled blocks, validation and dense kernel for what is
+    # left) + rollout + reduce, not 12 separate evaluations
+    assert gpu_ctx.launches - launches0 <= 10 * 10
     scores = np.array([r["score"] for r in res.all_results])
     assert res.best_score == scores.max() and scores[-24:].mean() > scores[:12].mean()
     lo = np.array([5e-5, 5e-5, 10.0]), np.array([5e-4, 5e-4, 25.0])

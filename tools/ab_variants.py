@@ -122,7 +122,8 @@ def one(E):
 
 
 def one_dare(batch):
-    r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_dare.py"), str(batch), "brief"], capture_output=True, text=True)
+    extra = [os.environ["QT_DARE_SIZES"]] if os.environ.get("QT_DARE_SIZES") else []
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_dare.py"), str(batch), "brief", *extra], capture_output=True, text=True)
     print(r.stdout.strip().replace("\n", "   ") or r.stderr[-400:])
 
 
