@@ -288,6 +288,7 @@ def run_reference_arm(args) -> None:
 
 
 DARE_SIZES = ((6, 65536), (9, 65536), (12, 16384), (15, 16384))   # (n, systems per GPU); m = 4 throughout
+DARE_LARGE_BATCH = 1 << 20   # second batch size for n = 6 / 9: launch overhead and the partial last wave amortised
 
 
 def run_dare_section(ctx, rank: int, world: int, fp64_tflops: float, barrier) -> dict:
@@ -320,17 +321,39 @@ def run_dare_section(ctx, rank: int, world: int, fp64_tflops: float, barrier) ->
         K = torch.empty((batch, 4, n), **f64)
         iters = torch.zeros(batch, dtype=torch.int32, device=dev)
         info = torch.zeros(batch, dtype=torch.int32, device=dev)
-        for _ in range(3):
-            ctx.dare_batched(n, 4, batch, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        d0.record()
-        for _ in range(reps):
-            ctx.dare_batched(n, 4, batch, A, 0, B, 0, Q, n * n, R, 16, None, K, iters, info)
-        d1.record()
-        barrier()
-        ms = d0.elapsed_time(d1) / reps
+
+        def timed(nb, Qx, Rx, Kx, itx, infx):
+            for _ in range(3):
+                ctx.dare_batched(n, 4, nb, A, 0, B, 0, Qx, n * n, Rx, 16, None, Kx, itx, infx)
+            barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            d0.record()
+            for _ in range(reps):
+                ctx.dare_batched(n, 4, nb, A, 0, B, 0, Qx, n * n, Rx, 16, None, Kx, itx, infx)
+            d1.record()
+            barrier()
+            return d0.elapsed_time(d1) / reps
+
+        ms = timed(batch, Q, R, K, iters, info)          # the shipped path (QT_DARE_PATH_AUTO)
+        ms_dense = ms_big = None
+        if n <= 9:
+            # the reference's designs take the decoupled path (blocks in registers): also time the dense kernel on the
+            # same systems, and the shipped path on a batch large enough to amortise launches and the partial last wave
+            K_auto = K.clone()
+            ctx.set_dare_path(1)
+            try:
+                ms_dense = timed(batch, Q, R, K, iters, info)
+            finally:
+                ctx.set_dare_path(0)
+            paths_rel = float(((K - K_auto).abs().amax(dim=(1, 2)) / K_auto.abs().amax(dim=(1, 2))).max().item())
+            big = DARE_LARGE_BATCH
+            Qb, Rb = Q.repeat(big // batch, 1, 1), R.repeat(big // batch, 1, 1)
+            Kb = torch.empty((big, 4, n), **f64)
+            ib, fb = torch.zeros(big, dtype=torch.int32, device=dev), torch.zeros(big, dtype=torch.int32, device=dev)
+            ms_big = timed(big, Qb, Rb, Kb, ib, fb)
+            del Qb, Rb, Kb, ib, fb
+            ms = timed(batch, Q, R, K, iters, info)      # leaves K / iters / info of the shipped path for the checks below
         # e2e: pinned host matrices in, host gains / info out, through the C ABI (qt_dare_host)
         Ah, Bh, Qh, Rh = (t.cpu().pin_memory() for t in (A, B, Q, R))
         Kh = torch.empty((batch, 4, n), dtype=torch.float64).pin_memory()
@@ -344,22 +367,46 @@ def run_dare_section(ctx, rank: int, world: int, fp64_tflops: float, barrier) ->
         barrier()
         e2e_s = (time.perf_counter() - w0) / e_reps
         same = bool(torch.equal(Kh, K.cpu()))
-        t = torch.tensor([ms, e2e_s * 1e3], **f64)
+        t = torch.tensor([ms, e2e_s * 1e3, ms_dense or 0.0, ms_big or 0.0], **f64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0].item()), float(t[1].item())
+        ms, e2e_ms, ms_dense, ms_big = (float(x) for x in t.tolist())
         k = float(iters.double().mean().item())
         rate = world * batch / (ms * 1e-3)
-        tflops = rate * w_dare(n, 4, k) / 1e12
+        decoupled = n <= 9
+        # flops of the path that ran: three (n / 3)-state single-input blocks on the decoupled path, the n x n recursion
+        # on the dense one (W_dare of SURVEY 8(d) in both cases)
+        flops = 3.0 * w_dare(n // 3, 1, k) if decoupled else w_dare(n, 4, k)
+        tflops = rate * flops / 1e12
+        bytes_per_solve = 8 * (n * n + 16) + 8 * 4 * n + 8      # Q, R in; K, iters, info out (A and B are shared)
+        entry_extra = {}
+        if decoupled:
+            peak = world * fp64_tflops
+            dense_rate = world * batch / (ms_dense * 1e-3)
+            big_rate = world * DARE_LARGE_BATCH / (ms_big * 1e-3)
+            entry_extra = {
+                "path": "decoupled (dare_blocks_kernel: 3 blocks of %d states per system, in registers)" % (n // 3),
+                "hbm": {"bytes_per_solve": bytes_per_solve, "achieved_gbs": rate * bytes_per_solve / 1e9},
+                "large_batch": {"batch_per_gpu": DARE_LARGE_BATCH, "value": big_rate, "ms_per_launch": ms_big,
+                                "fp64_tflops": big_rate * flops / 1e12,
+                                "fp64_frac": big_rate * flops / 1e12 / peak if peak > 0 else None,
+                                "hbm_gbs": big_rate * bytes_per_solve / 1e9},
+                "dense_path": {"value": dense_rate, "ms_per_launch": ms_dense, "kernel": "dare_kernel<N, R> (QT_DARE_PATH_DENSE)",
+                               "max_rel_diff_of_K_between_paths": paths_rel,
+                               "roofline": {"bound": "fp64", "achieved": dense_rate * w_dare(n, 4, k) / 1e12, "peak": peak,
+                                            "unit": "TFLOP/s", "flops_per_solve": w_dare(n, 4, k),
+                                            "frac": dense_rate * w_dare(n, 4, k) / 1e12 / peak if peak > 0 else None}}}
+        else:
+            entry_extra = {"path": "dense (dare_kernel<N, R>)"}
         out["sizes"][f"n{n}"] = {
-            "n": n, "m": 4, "systems": what, "batch_per_gpu": batch, "value": rate, "ms_per_launch": ms,
+            "n": n, "m": 4, "systems": what, "batch_per_gpu": batch, "value": rate, "ms_per_launch": ms, **entry_extra,
             "mean_doubling_iterations": k, "failed": int((info != 0).sum().item()),
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "solves/s", "api": "qt_dare_host (C ABI, pinned host buffers)",
                     "h2d_bytes_per_step": 8 * (n * n + 4 * n + batch * (n * n + 16)), "d2h_bytes_per_step": batch * (8 * 4 * n + 8),
                     "matches_device_resident_result": same},
             "roofline": {"bound": "fp64", "achieved": tflops, "peak": world * fp64_tflops, "unit": "TFLOP/s",
                          "frac": tflops / (world * fp64_tflops) if fp64_tflops > 0 else None,
-                         "flops_per_solve": w_dare(n, 4, k)}}
+                         "flops_per_solve": flops}}
     head = out["sizes"]["n6"]
     out.update({"value": head["value"], "batch": head["batch_per_gpu"], "ms_per_launch": head["ms_per_launch"],
                 "mean_doubling_iterations": head["mean_doubling_iterations"], "failed": head["failed"], "e2e": head["e2e"],
