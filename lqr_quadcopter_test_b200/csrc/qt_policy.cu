@@ -22,6 +22,7 @@
 //    load per two FFMA2); the last hidden layer is never stored — each chunk of it is multiplied
 //    into the four output accumulators as soon as it is activated.
 #include "qt_common.cuh"
+#include "qt_policy_tc.cuh"
 #include "qt_step.cuh"
 
 namespace qt {
@@ -52,6 +53,7 @@ struct MlpDesc {
     int t_total;                     // floats of the staged weights
     int t_buf[2];                    // rows (of 32 floats) of the two per-warp activation buffers
     int t_inplace;                   // every hidden layer is one 64-unit column tile: the layers run in place in buffer 0
+    int tc_ok;                       // two hidden layers of at most 64 units: the tensor-core evaluation applies (qt_policy_tc.cuh)
 };
 
 static bool describe(const qt_mlp &m, MlpDesc &d) {
@@ -100,6 +102,7 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
     d.t_buf[0] += 2;     // tile_layer's operand prefetch runs two rows past the layer's input
     if (d.t_buf[1]) d.t_buf[1] += 2;
     d.tiled = m.n_layers >= 2 && fma_tiled * 4 <= fma_packed * 5;   // at most 25 % padding work
+    d.tc_ok = m.n_layers == 3 && m.dims[1] <= tc::kN && m.dims[2] <= tc::kN;
     return true;
 }
 
@@ -438,6 +441,132 @@ __device__ __forceinline__ void make_features(const double (&s)[12], const doubl
     }
 }
 
+// ---- tensor-core evaluation (qt_policy_tc.cuh) ------------------------------------------------------
+// Stage the packed weights for the tensor-core evaluation: both hidden layers as B operands (unit n, input k) in the
+// canonical K-major layout, split into TF32 head and tail; the output layer and the biases as plain fp32.
+__device__ __forceinline__ void stage_weights_tc(const MlpDesc &M, const float *__restrict__ Wg, float *smem) {
+    for (int l = 0; l < 2; l++) {
+        const int K = l == 0 ? tc::kK0 : tc::kK1, rows = M.rows[l], outp = M.outp[l];
+        const float *src = Wg + M.w_off[l];
+        float *hi = smem + (l == 0 ? tc::kB0Hi : tc::kB1Hi), *lo = smem + (l == 0 ? tc::kB0Lo : tc::kB1Lo);
+        for (int i = threadIdx.x; i < K * tc::kN; i += blockDim.x) {
+            const int k = i / tc::kN, n = i - k * tc::kN;
+            const float w = (k < rows && n < outp) ? src[k * outp + n] : 0.0f;
+            float h, t;
+            tc::split_tf32(w, h, t);
+            const int at = ((k >> 2) * tc::kN + n) * 4 + (k & 3);
+            hi[at] = h;
+            lo[at] = t;
+        }
+        for (int n = threadIdx.x; n < tc::kN; n += blockDim.x)
+            smem[tc::kBias + l * tc::kN + n] = n < outp ? src[rows * outp + n] : 0.0f;
+    }
+    {
+        const int rows = M.rows[2], outp = M.outp[2];   // outp = 4
+        const float *src = Wg + M.w_off[2];
+        for (int i = threadIdx.x; i < tc::kN * 4; i += blockDim.x) {
+            const int k = i >> 2, j = i & 3;
+            smem[tc::kW3 + i] = k < rows ? src[k * outp + j] : 0.0f;
+        }
+        if (threadIdx.x < 4) smem[tc::kBias + 2 * tc::kN + threadIdx.x] = src[rows * outp + threadIdx.x];
+    }
+}
+
+// Second half of a hidden layer on the tensor cores: read this thread's 64 accumulators, add the bias, activate.
+// NEXT_A: store the result as the next layer's A operand; else multiply it into the four output accumulators.
+template <int KIND, bool NEXT_A>
+__device__ __forceinline__ void tc_epilogue(float *smem, uint32_t taddr, const float *bias, int row, float (&o)[4]) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        float d[32];
+        tc::tmem_ld32(taddr + half * 32, d);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + half * 32 + j);
+            const float h0 = activate_t<KIND>(d[j] + b.x), h1 = activate_t<KIND>(d[j + 1] + b.y);
+            const float h2 = activate_t<KIND>(d[j + 2] + b.z), h3 = activate_t<KIND>(d[j + 3] + b.w);
+            if (NEXT_A) {
+                tc::store_chunk(smem, row, (half * 32 + j) >> 2, h0, h1, h2, h3);
+            } else {
+                const float h[4] = {h0, h1, h2, h3};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 w = *reinterpret_cast<const float4 *>(smem + tc::kW3 + (half * 32 + j + q) * 4);
+                    o[0] = fmaf(h[q], w.x, o[0]);
+                    o[1] = fmaf(h[q], w.y, o[1]);
+                    o[2] = fmaf(h[q], w.z, o[2]);
+                    o[3] = fmaf(h[q], w.w, o[3]);
+                }
+            }
+        }
+    }
+}
+
+// PolicyNetwork.forward for the 128 episodes of the block; every thread of the block must call it after having
+// stored its feature row with tc_store_features and passed the block barrier that follows.
+template <int KIND>
+__device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *smem, uint32_t tmem_base, uint32_t &phase,
+                                                    float (&out)[4]) {
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + tc::kBar);
+    const int row = threadIdx.x;
+    const uint32_t taddr = tmem_base + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
+    float o[4];
+    if (threadIdx.x == 0) {
+        tc::fence_after_sync();
+        tc::issue_layer(smem, tc::kB0Hi, tc::kB0Lo, tc::kK0 / 8, tmem_base, bar);
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    tc_epilogue<KIND, true>(smem, taddr, smem + tc::kBias, row, o);
+    tc::fence_before_sync();     // this thread's tcgen05.ld are done before the next MMAs overwrite the accumulator
+    tc::fence_async_smem();      // ... and its new A rows are visible to the tensor core
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc::fence_after_sync();
+        tc::issue_layer(smem, tc::kB1Hi, tc::kB1Lo, tc::kK1 / 8, tmem_base, bar);
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    {
+        const float4 b = *reinterpret_cast<const float4 *>(smem + tc::kBias + 2 * tc::kN);
+        o[0] = b.x;
+        o[1] = b.y;
+        o[2] = b.z;
+        o[3] = b.w;
+    }
+    tc_epilogue<KIND, false>(smem, taddr, smem + tc::kBias + tc::kN, row, o);
+    tc::fence_before_sync();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float sg = 1.0f / (1.0f + expf(-o[i]));  // torch.sigmoid
+        out[i] = fmaf(sg, M.out_scale[i], M.out_lo[i]);
+    }
+}
+
+__device__ __forceinline__ void mlp_forward_tc(const MlpDesc &M, float *smem, uint32_t tmem_base, uint32_t &phase,
+                                               float (&out)[4]) {
+    switch (M.activation) {
+    case QT_ACT_TANH: mlp_forward_tc_kind<QT_ACT_TANH>(M, smem, tmem_base, phase, out); break;
+    case QT_ACT_ELU: mlp_forward_tc_kind<QT_ACT_ELU>(M, smem, tmem_base, phase, out); break;
+    case QT_ACT_LEAKY_RELU: mlp_forward_tc_kind<QT_ACT_LEAKY_RELU>(M, smem, tmem_base, phase, out); break;
+    default: mlp_forward_tc_kind<QT_ACT_RELU>(M, smem, tmem_base, phase, out); break;
+    }
+}
+
+// the 18 features of this thread's episode as chunks 0..5 of its A row (features 18..23 are zero padding)
+__device__ __forceinline__ void tc_store_features(float *smem, const float (&f)[QT_FEATURE_DIM]) {
+    const int row = threadIdx.x;
+    tc::store_chunk(smem, row, 0, f[0], f[1], f[2], f[3]);
+    tc::store_chunk(smem, row, 1, f[4], f[5], f[6], f[7]);
+    tc::store_chunk(smem, row, 2, f[8], f[9], f[10], f[11]);
+    tc::store_chunk(smem, row, 3, f[12], f[13], f[14], f[15]);
+    tc::store_chunk(smem, row, 4, f[16], f[17], 0.0f, 0.0f);
+    tc::store_chunk(smem, row, 5, 0.0f, 0.0f, 0.0f, 0.0f);
+    tc::fence_async_smem();
+}
+
 struct PolicyArgs {
     int64_t E, k_stride;
     int max_steps, w_in_smem, teacher;  // teacher: 0 none, else 1 + CtrlKind
@@ -461,16 +590,31 @@ __device__ __forceinline__ void stage_weights(const MlpDesc &M, const float *Wg,
 // network 2.40e9 against 2.19e9 env-steps/s); when the weights are too large to stage and stream from
 // L1/L2 instead, the deeper load prefetch that 255 registers allow wins (128-128: 4.0e8 against 2.4e8).
 // TILED: the warp-cooperative evaluation (64 accumulators per lane, two blocks per SM).
-template <int MOTION, int MINB, bool TILED>
+// EVAL: 0 one episode per thread, 1 warp-cooperative tiles (both on the FP32 pipe, bit-identical), 2 the hidden layers
+// on the tensor cores (qt_policy_tc.cuh; the block's 128 episodes are one MMA operand, two blocks per SM).
+template <int MOTION, int MINB, int EVAL>
 __global__ void __launch_bounds__(kPolicyThreads, MINB)
     rollout_policy_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                           const __grid_constant__ MlpDesc M, const __grid_constant__ PolicyArgs A) {
     extern __shared__ __align__(16) float smem_f[];
     constexpr int T = kPolicyThreads;
+    constexpr bool TILED = EVAL == 1, TC = EVAL == 2;
+    static_assert(!TC || T == tc::kRows, "the tensor-core evaluation maps one block to one M = 128 operand");
     const int64_t E = A.E;
     const int64_t e_raw = (int64_t)blockIdx.x * T + threadIdx.x;
-    float *tile0, *tile1;
-    if constexpr (TILED) {
+    float *tile0 = nullptr, *tile1 = nullptr;
+    uint32_t tmem_base = 0u, mma_phase = 0u;
+    if constexpr (TC) {
+        stage_weights_tc(M, A.W, smem_f);
+        uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_f + tc::kBar + 2);
+        if (threadIdx.x < 32) tc::tmem_alloc(tmem_slot);
+        if (threadIdx.x == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(smem_f + tc::kBar), 1);
+        tc::fence_async_smem();      // the staged weights are read by the tensor core
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        tmem_base = *tmem_slot;
+    } else if constexpr (TILED) {
         stage_weights_tiled(M, A.W, smem_f);
         float *wb = smem_f + M.t_total + (threadIdx.x >> 5) * (M.t_buf[0] + M.t_buf[1]) * 32;
         tile0 = wb;
@@ -482,8 +626,8 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
         tile1 = tile0 + M.tile_w[0] * T;
         if (e_raw >= E) return;
     }
-    // TILED: the lanes past the last episode stay, because the whole warp evaluates the network together;
-    // they shadow the last episode and never write
+    // TILED / TC: the lanes past the last episode stay, because the whole warp (block) evaluates the network
+    // together; they shadow the last episode and never write
     const bool valid = e_raw < E;
     const int64_t e = valid ? e_raw : E - 1;
 
@@ -515,14 +659,19 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
 
     bool alive = valid && A.max_steps > 0;
     while (true) {
-        if constexpr (TILED) {
+        float feat[QT_FEATURE_DIM];
+        if constexpr (TC) {
+            // the block leaves together; the barrier that takes the vote also publishes the feature rows
+            make_features(s, tp, tv, feat);
+            tc_store_features(smem_f, feat);
+            if (!__syncthreads_or(alive)) break;
+        } else if constexpr (TILED) {
             if (!__any_sync(0xffffffffu, alive)) break;
         } else {
             if (!alive) break;
         }
         // ---- the policy acts on the pre-step observation
-        float feat[QT_FEATURE_DIM];
-        make_features(s, tp, tv, feat);
+        if constexpr (!TC) make_features(s, tp, tv, feat);
         const bool log_data = alive && A.feat && step == next_data && data_slot < A.data_slots;
         if (log_data) {
             float *f = A.feat + ((int64_t)data_slot * E + e) * QT_FEATURE_DIM;
@@ -530,13 +679,15 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
             for (int i = 0; i < QT_FEATURE_DIM; i += 2) *reinterpret_cast<float2 *>(f + i) = make_float2(feat[i], feat[i + 1]);
         }
         float out[4];
-        if constexpr (TILED)
+        if constexpr (TC)
+            mlp_forward_tc(M, smem_f, tmem_base, mma_phase, out);
+        else if constexpr (TILED)
             mlp_forward_tiled(M, smem_f, tile0, tile1, feat, out);
         else if (A.w_in_smem)   // two inlined copies: one reads the weights with LDS, the other with LDG
             mlp_forward<T>(M, smem_f, tile0, tile1, feat, out);
         else
             mlp_forward<T>(M, A.W, tile0, tile1, feat, out);
-        if (!alive) continue;   // TILED only: this lane's episode is over, it only helps the warp
+        if (!alive) continue;   // TILED / TC only: this lane's episode is over, it only helps the warp / block
         double act[4] = {(double)out[0], (double)out[1], (double)out[2], (double)out[3]};
 
         // ---- supervisor label on the same observation (train.py:682-696)
@@ -625,6 +776,11 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
         err_pre = err_post;
         alive = term == QT_TERM_NONE && step < A.max_steps;
     }
+    if constexpr (TC) {
+        tc::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base);
+    }
     if (!valid) return;
     if (in_phase && streak >= P.overshoot_window) {
         ov_count += 1;
@@ -710,14 +866,14 @@ static size_t smem_plan_tiled(const MlpDesc &M) {
     return ((size_t)M.t_total + (size_t)(kPolicyThreads / 32) * (M.t_buf[0] + M.t_buf[1]) * 32) * sizeof(float);
 }
 
-template <int MOTION, int MINB, bool TILED>
+template <int MOTION, int MINB, int EVAL>
 static cudaError_t launch_policy_as(const qt_params &P, const DynConsts &C, const MlpDesc &M, const PolicyArgs &A,
                                     size_t smem, cudaStream_t st) {
     const int64_t blocks = (A.E + kPolicyThreads - 1) / kPolicyThreads;
-    cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, MINB, TILED>,
+    cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, MINB, EVAL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_policy_kernel<MOTION, MINB, TILED><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    rollout_policy_kernel<MOTION, MINB, EVAL><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
     return cudaGetLastError();
 }
 
@@ -726,20 +882,22 @@ static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, PolicyArg
     DynConsts C;
     C.init(P);
     too_wide = false;
+    if (M.tc_ok && (P.debug_flags & QT_FLAG_POLICY_TENSOR_CORES) && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD))
+        return launch_policy_as<MOTION, 2, 2>(P, C, M, A, (size_t)tc::kFloats * sizeof(float), st);
     if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024) {
         // three resident blocks (168 registers, the env state spills to L1 across the network evaluation)
         // when the shared memory allows, else two or one
         if (QT_POLICY_TILED_3 && smem_plan_tiled(M) <= 74 * 1024)
-            return launch_policy_as<MOTION, 3, true>(P, C, M, A, smem_plan_tiled(M), st);
-        return launch_policy_as<MOTION, 2, true>(P, C, M, A, smem_plan_tiled(M), st);
+            return launch_policy_as<MOTION, 3, 1>(P, C, M, A, smem_plan_tiled(M), st);
+        return launch_policy_as<MOTION, 2, 1>(P, C, M, A, smem_plan_tiled(M), st);
     }
     const size_t smem = smem_plan(M, A.w_in_smem);
     if (smem > 200 * 1024) {
         too_wide = true;
         return cudaSuccess;
     }
-    if (A.w_in_smem && smem <= 72 * 1024) return launch_policy_as<MOTION, 3, false>(P, C, M, A, smem, st);
-    return launch_policy_as<MOTION, 2, false>(P, C, M, A, smem, st);
+    if (A.w_in_smem && smem <= 72 * 1024) return launch_policy_as<MOTION, 3, 0>(P, C, M, A, smem, st);
+    return launch_policy_as<MOTION, 2, 0>(P, C, M, A, smem, st);
 }
 
 }  // namespace qt

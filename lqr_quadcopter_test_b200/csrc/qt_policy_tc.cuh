@@ -1,0 +1,164 @@
+// qt_policy_tc.cuh — the two hidden layers of the deep tracking policy on the 5th-generation tensor cores
+// (controllers/deep_tracking_policy.py:114-147, PolicyNetwork.forward).
+//
+// A block of 128 threads = 128 episodes is one M = 128 operand: episode i is row i of A and lane i of the
+// accumulator in tensor memory.  Per env step and layer:
+//   every thread splits its activation row into a TF32 head and tail (x = hi + lo, hi = cvt.rna.tf32(x),
+//   lo = x - hi exactly) and stores both into shared memory in the canonical K-major core-matrix layout
+//   (no swizzle: 8 rows x 16 bytes per core matrix; the 16-byte chunk c of row m lives at (c * 128 + m) * 16, so a
+//   warp's 16-byte stores are consecutive and conflict free);
+//   one thread issues, per k-step of 8, the three `tcgen05.mma.cta_group::1.kind::tf32` of the 3xTF32 scheme
+//   (A_lo B_hi + A_hi B_lo + A_hi B_hi; the weights were split once when the block staged them; fp32 accumulation
+//   in TMEM) and a `tcgen05.commit` onto an mbarrier;
+//   every thread waits on the mbarrier, reads its own 64 accumulators with `tcgen05.ld.32x32b` (warp w owns TMEM
+//   lanes 32 w .. 32 w + 31), adds the bias and applies the activation.
+// The 64 -> 4 output layer stays on the FP32 pipe, from registers (256 FMAs per episode: a tensor-core round trip
+// would cost more than it saves, and this keeps torch's order of summation for that layer).
+// Accuracy: dropping lo * lo and the truncation of lo to 11 bits leave a relative error of about 2^-21 per product —
+// the size of fp32 summation-order noise in a 64-term dot product — so this evaluation is NOT bit-identical to the
+// FP32-pipe evaluations (qt_policy.cu), which remain the default and the parity path; the tests bound the difference.
+// Shapes: two hidden layers of at most 64 units (the reference's default 64-64), zero padded to 64.
+// Shared memory per block: A 64 KB (hi + lo, K = 64) + weights 44 KB (18->64 and 64->64, hi + lo) + 2 KB: two
+// blocks per SM.  TMEM: 64 columns per block.
+#pragma once
+#include <stdint.h>
+
+namespace qt {
+namespace tc {
+
+constexpr int kRows = 128;                 // episodes per block = M of the MMA
+constexpr int kN = 64;                     // hidden width (padded)
+constexpr int kK0 = 24;                    // 18 features padded to a multiple of the MMA's K = 8
+constexpr int kK1 = 64;
+constexpr int kTmemCols = 64;
+// float offsets into the block's shared memory
+constexpr int kAHi = 0;                                  // [16 chunks][128 rows][4]
+constexpr int kALo = kAHi + kRows * kK1;
+constexpr int kB0Hi = kALo + kRows * kK1;                // [6 chunks][64 units][4]
+constexpr int kB0Lo = kB0Hi + kN * kK0;
+constexpr int kB1Hi = kB0Lo + kN * kK0;                  // [16 chunks][64 units][4]
+constexpr int kB1Lo = kB1Hi + kN * kK1;
+constexpr int kW3 = kB1Lo + kN * kK1;                    // [64][4] output layer
+constexpr int kBias = kW3 + kN * 4;                      // b1[64] b2[64] b3[4]
+constexpr int kBar = kBias + 2 * kN + 4;                 // mbarrier (8 bytes, 8-byte aligned) + TMEM base address
+constexpr int kFloats = kBar + 4;
+static_assert(kBar % 2 == 0, "mbarrier alignment");
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+// both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, K-major: start address >> 4 at bit 0,
+// leading byte offset (between the two 16-byte K chunks of one MMA) >> 4 at bit 16, stride byte offset (between
+// groups of 8 rows) >> 4 at bit 32, descriptor version 1 at bit 46
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {   // one whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t base) {      // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(kTmemCols) : "memory");
+}
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi the nearest TF32 (ties away) and lo = x - hi exact in fp32 (the MMA reads lo's top 19 bits)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// store four consecutive K values of this thread's row (chunk c) as head and tail
+__device__ __forceinline__ void store_chunk(float *smem, int row, int c, float x0, float x1, float x2, float x3) {
+    float4 hi, lo;
+    split_tf32(x0, hi.x, lo.x);
+    split_tf32(x1, hi.y, lo.y);
+    split_tf32(x2, hi.z, lo.z);
+    split_tf32(x3, hi.w, lo.w);
+    *reinterpret_cast<float4 *>(smem + kAHi + (c * kRows + row) * 4) = hi;
+    *reinterpret_cast<float4 *>(smem + kALo + (c * kRows + row) * 4) = lo;
+}
+
+// one layer's MMAs: D[128][64] = A[128][K] B[64][K]', three TF32 products per k-step of 8; thread 0 of the block
+__device__ __forceinline__ void issue_layer(const float *smem, int b_hi, int b_lo, int ksteps, uint32_t d_tmem, uint64_t *bar) {
+    const uint32_t a_hi = smem_u32(smem + kAHi), a_lo = smem_u32(smem + kALo);
+    const uint32_t bh = smem_u32(smem + b_hi), bl = smem_u32(smem + b_lo);
+    constexpr uint32_t kALbo = kRows * 16, kBLbo = kN * 16, kSbo = 128;
+    for (int ks = 0; ks < ksteps; ks++) {
+        const uint64_t dah = smem_desc(a_hi + ks * 2 * kALbo, kALbo, kSbo), dal = smem_desc(a_lo + ks * 2 * kALbo, kALbo, kSbo);
+        const uint64_t dbh = smem_desc(bh + ks * 2 * kBLbo, kBLbo, kSbo), dbl = smem_desc(bl + ks * 2 * kBLbo, kBLbo, kSbo);
+        mma_tf32(d_tmem, dal, dbh, ks > 0 ? 1u : 0u);
+        mma_tf32(d_tmem, dah, dbl, 1u);
+        mma_tf32(d_tmem, dah, dbh, 1u);
+    }
+    mma_commit(bar);
+}
+
+}  // namespace tc
+}  // namespace qt

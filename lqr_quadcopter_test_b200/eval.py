@@ -82,6 +82,8 @@ def rollout_device(controller, env_config: EnvConfig, criteria, seeds, max_steps
         out["features"] = torch.zeros((data_slots, E, P.FEATURE_DIM), dtype=torch.float32, device=dev)
         out["actions"] = torch.zeros((data_slots, E, P.ACTION_DIM), dtype=torch.float32, device=dev)
     if is_policy:
+        if getattr(controller, "tensor_cores", False):
+            prm.debug_flags |= P.FLAG_POLICY_TENSOR_CORES
         ctx.rollout_policy(prm, E, max_steps, state0, tparams, controller.packed_mlp(),
                            K.contiguous() if K is not None else None, k_cols, k_stride, out["metrics"],
                            out.get("final_state"), out.get("traj"), max(record_stride, 1), traj_slots,

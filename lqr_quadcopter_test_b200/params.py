@@ -13,6 +13,8 @@ TERMINATION_REASONS = {0: "", 1: "time_limit", 2: "position_bounds", 3: "numeric
 
 STATE_DIM, ACTION_DIM, TARGET_PARAMS, OBS_DIM = 12, 4, 12, 22
 METRICS_DIM, TRAJ_FIELDS, FEATURE_DIM, INFO_DIM = 16, 24, 18, 4
+# qt_params.debug_flags bits (include/qtrack.h)
+DEBUG_GENERAL_PATH, DEBUG_POLICY_PER_THREAD, FLAG_POLICY_TENSOR_CORES = 1, 2, 4
 
 # rows of the metric vector (enum qt_metric)
 (M_STEPS, M_FINAL_TIME, M_ENV_ON_TARGET, M_MET_ON_TARGET, M_SUM_ERR, M_MAX_ERR, M_SUM_ERR2,

@@ -185,3 +185,23 @@ def test_batch_edges_and_optional_outputs(gpu_ctx, batch):
     (Pn, Kn, _, _), _ = _both(gpu_ctx, A, B, Q, R, want_P=False)
     assert Pn is None and (Kn == K0).all()
     assert not i0.any() and max(_rel(K0[i], K1[i]) for i in range(batch)) <= REL
+
+
+def test_failure_behaviour_follows_scipy(gpu_ctx):
+    """Where scipy.linalg.solve_discrete_are (the reference's solver, riccati_lqr.py:165) raises, info != 0 — an
+    undriven mode on or outside the unit circle; where it returns a solution that is not stabilising without raising
+    — an unobservable mode ON the unit circle — both paths return that same solution with info = 0 (no extra
+    stability test: the drop-in must not reject what the reference accepts)."""
+    from scipy.linalg import solve_discrete_are
+
+    A, B, Q, R = np.diag([1.0, 0.5]), np.array([[1.0], [1.0]]), np.diag([0.0, 1.0]), np.eye(1)
+    Ps = solve_discrete_are(A, B, Q, R)
+    for (P, K, _, info) in _both(gpu_ctx, A, B, Q[None], R[None]):
+        assert info[0] == 0
+        np.testing.assert_allclose(P[0], Ps, rtol=0, atol=1e-12)
+    for lam in (1.0, 1.2):
+        A2, B2 = np.diag([lam, 0.5]), np.array([[0.0], [1.0]])
+        with pytest.raises(np.linalg.LinAlgError):
+            solve_discrete_are(A2, B2, np.eye(2), np.eye(1))
+        for (_, _, _, info) in _both(gpu_ctx, A2, B2, np.eye(2)[None], np.eye(1)[None]):
+            assert info[0] != 0

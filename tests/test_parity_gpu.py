@@ -447,3 +447,42 @@ def test_randomised_configurations_match_oracle(golden, gb, orc):
         if not noisy:
             worst = max(worst, float(np.abs(got["final_state"] - ref["final_state"]).max()))
     print(f"[parity] {n_trials} randomised configurations: max |final state diff| = {worst:.2e} (figure-8 + feedforward excluded)")
+
+
+@pytest.mark.parametrize("hidden,act,motion", [([64, 64], "relu", "linear"), ([48, 64], "tanh", "circular"),
+                                               ([64, 20], "elu", "stationary"), ([64, 64], "leaky_relu", "figure8")])
+def test_tensor_core_policy_evaluation_is_close_to_the_fp32_pipe(golden, gb, orc, hidden, act, motion):
+    """QT_FLAG_POLICY_TENSOR_CORES: the two hidden layers as tcgen05 TF32 MMAs with the 3xTF32 split (x = hi + lo,
+    fp32 accumulation in TMEM) against the FP32-pipe evaluation.  Not bit-identical by construction: each product
+    carries about 2^-21 relative error.  Bounds: the action on the SAME observation (first step of every episode)
+    within 4e-6 of the action range; a 40-step rollout within 1e-5 in every state; the logged teacher labels (which
+    depend on the visited states only) within 1e-4.  1000 episodes: a partial last block, finished and shadow lanes."""
+    import copy
+
+    import torch
+
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy
+
+    torch.manual_seed(len(hidden) * 77 + hidden[1])
+    pol = DeepTrackingPolicy(config={"hidden_sizes": hidden, "activation": act})
+    E = 1000
+    env = EnvConfig()
+    env.target.motion_type = motion
+    prm = P.make_params(env, gc.controller_ns())
+    tcp = copy.copy(prm)
+    tcp.debug_flags = 4
+    s0, tp = orc.reset_reference(prm, np.arange(900, 900 + E))
+    K = golden["dare"]["lqr_default_K"]
+    a = gb.rollout_policy(prm, s0, tp, pol, K=K, max_steps=40, data_stride=7, traj_stride=1)
+    b = gb.rollout_policy(tcp, s0, tp, pol, K=K, max_steps=40, data_stride=7, traj_stride=1)
+    act0_a, act0_b = a["traj"][0, P.TRAJ_ACTION:P.TRAJ_ACTION + 4], b["traj"][0, P.TRAJ_ACTION:P.TRAJ_ACTION + 4]
+    scale = np.array([20.0, 6.0, 6.0, 6.0])[:, None]
+    d_act = float((np.abs(act0_a - act0_b) / scale).max())
+    d_state = float(np.abs(a["final_state"] - b["final_state"]).max())
+    print(f"[parity] tensor-core policy {hidden}/{act}/{motion}: first action diff {d_act:.2e} of range, "
+          f"final state diff after 40 steps {d_state:.2e}, identical first actions {int((act0_a == act0_b).all(axis=0).sum())}/{E}")
+    assert np.isfinite(b["final_state"]).all() and (b["metrics"][P.M_STEPS] == a["metrics"][P.M_STEPS]).all()
+    assert 0.0 < d_act <= 4e-6        # > 0: the tensor-core path really ran (the FP32 paths are bit-identical to each other)
+    assert d_state <= 1e-5
+    np.testing.assert_array_equal(a["features"][0], b["features"][0])
+    np.testing.assert_allclose(a["actions"], b["actions"], rtol=0, atol=1e-4)
