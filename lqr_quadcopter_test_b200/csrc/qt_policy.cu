@@ -473,12 +473,14 @@ __device__ __forceinline__ void stage_weights_tc(const MlpDesc &M, const float *
 }
 
 // Second half of a hidden layer on the tensor cores: read this thread's 64 accumulators, add the bias, activate.
-// NEXT_A: store the result as the next layer's A operand; else multiply it into the four output accumulators.
+// NEXT_A: store the result as the next layer's A operand (heads to shared memory, tails to the set's TMEM columns);
+// else multiply it into the four output accumulators.
 template <int KIND, bool NEXT_A>
-__device__ __forceinline__ void tc_epilogue(float *smem, uint32_t taddr, const float *bias, int row, float (&o)[4]) {
+__device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t taddr, const float *bias, int row, float (&o)[4]) {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         float d[32];
+        [[maybe_unused]] float lo[32];
         tc::tmem_ld32(taddr + half * 32, d);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -486,7 +488,7 @@ __device__ __forceinline__ void tc_epilogue(float *smem, uint32_t taddr, const f
             const float h0 = activate_t<KIND>(d[j] + b.x), h1 = activate_t<KIND>(d[j + 1] + b.y);
             const float h2 = activate_t<KIND>(d[j + 2] + b.z), h3 = activate_t<KIND>(d[j + 3] + b.w);
             if (NEXT_A) {
-                tc::store_chunk(smem, row, (half * 32 + j) >> 2, h0, h1, h2, h3);
+                tc::store_chunk(a_hi, row, (half * 32 + j) >> 2, h0, h1, h2, h3, lo + j);
             } else {
                 const float h[4] = {h0, h1, h2, h3};
 #pragma unroll
@@ -499,32 +501,36 @@ __device__ __forceinline__ void tc_epilogue(float *smem, uint32_t taddr, const f
                 }
             }
         }
+        if (NEXT_A) tc::tmem_st32(taddr + 64 + half * 32, lo);
     }
+    if (NEXT_A) tc::tmem_st_wait();
 }
 
-// PolicyNetwork.forward for the 128 episodes of the block; every thread of the block must call it after having
-// stored its feature row with tc_store_features and passed the block barrier that follows.
+// PolicyNetwork.forward for the 128 episodes of a set; every thread of the set must call it after having stored its
+// feature row with tc_store_features and passed the set barrier that follows.
 template <int KIND>
 __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *smem, uint32_t tmem_base, uint32_t &phase,
                                                     float (&out)[4]) {
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + tc::kBar);
-    const int row = threadIdx.x;
-    const uint32_t taddr = tmem_base + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
+    const int set = threadIdx.x / tc::kRows, row = threadIdx.x % tc::kRows;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + tc::kBar) + set;
+    float *a_hi = smem + tc::kAHi + set * tc::kRows * tc::kK1;
+    const uint32_t set_tmem = tmem_base + set * tc::kColsPerSet;
+    const uint32_t taddr = set_tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
     float o[4];
-    if (threadIdx.x == 0) {
+    if (row == 0) {
         tc::fence_after_sync();
-        tc::issue_layer(smem, tc::kB0Hi, tc::kB0Lo, tc::kK0 / 8, tmem_base, bar);
+        tc::issue_layer(smem, set, tc::kB0Hi, tc::kB0Lo, tc::kK0 / 8, set_tmem, bar);
     }
     tc::mbar_wait(bar, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    tc_epilogue<KIND, true>(smem, taddr, smem + tc::kBias, row, o);
-    tc::fence_before_sync();     // this thread's tcgen05.ld are done before the next MMAs overwrite the accumulator
-    tc::fence_async_smem();      // ... and its new A rows are visible to the tensor core
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    tc_epilogue<KIND, true>(smem, a_hi, taddr, smem + tc::kBias, row, o);
+    tc::fence_before_sync();     // this thread's tcgen05.ld / st are done before the next MMAs touch those columns
+    tc::fence_async_smem();      // ... and its new A heads are visible to the tensor core
+    tc::set_sync(1 + set);
+    if (row == 0) {
         tc::fence_after_sync();
-        tc::issue_layer(smem, tc::kB1Hi, tc::kB1Lo, tc::kK1 / 8, tmem_base, bar);
+        tc::issue_layer(smem, set, tc::kB1Hi, tc::kB1Lo, tc::kK1 / 8, set_tmem, bar);
     }
     tc::mbar_wait(bar, phase);
     phase ^= 1u;
@@ -536,7 +542,7 @@ __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *sme
         o[2] = b.z;
         o[3] = b.w;
     }
-    tc_epilogue<KIND, false>(smem, taddr, smem + tc::kBias + tc::kN, row, o);
+    tc_epilogue<KIND, false>(smem, a_hi, taddr, smem + tc::kBias + tc::kN, row, o);
     tc::fence_before_sync();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -556,14 +562,21 @@ __device__ __forceinline__ void mlp_forward_tc(const MlpDesc &M, float *smem, ui
 }
 
 // the 18 features of this thread's episode as chunks 0..5 of its A row (features 18..23 are zero padding)
-__device__ __forceinline__ void tc_store_features(float *smem, const float (&f)[QT_FEATURE_DIM]) {
-    const int row = threadIdx.x;
-    tc::store_chunk(smem, row, 0, f[0], f[1], f[2], f[3]);
-    tc::store_chunk(smem, row, 1, f[4], f[5], f[6], f[7]);
-    tc::store_chunk(smem, row, 2, f[8], f[9], f[10], f[11]);
-    tc::store_chunk(smem, row, 3, f[12], f[13], f[14], f[15]);
-    tc::store_chunk(smem, row, 4, f[16], f[17], 0.0f, 0.0f);
-    tc::store_chunk(smem, row, 5, 0.0f, 0.0f, 0.0f, 0.0f);
+__device__ __forceinline__ void tc_store_features(float *smem, uint32_t tmem_base, const float (&f)[QT_FEATURE_DIM]) {
+    const int set = threadIdx.x / tc::kRows, row = threadIdx.x % tc::kRows;
+    float *a_hi = smem + tc::kAHi + set * tc::kRows * tc::kK1;
+    float lo[32];
+#pragma unroll
+    for (int i = 20; i < 32; i++) lo[i] = 0.0f;
+    tc::store_chunk(a_hi, row, 0, f[0], f[1], f[2], f[3], lo + 0);
+    tc::store_chunk(a_hi, row, 1, f[4], f[5], f[6], f[7], lo + 4);
+    tc::store_chunk(a_hi, row, 2, f[8], f[9], f[10], f[11], lo + 8);
+    tc::store_chunk(a_hi, row, 3, f[12], f[13], f[14], f[15], lo + 12);
+    tc::store_chunk(a_hi, row, 4, f[16], f[17], 0.0f, 0.0f, lo + 16);
+    *reinterpret_cast<float4 *>(a_hi + (5 * tc::kRows + row) * 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    tc::tmem_st32(tmem_base + set * tc::kColsPerSet + 64 + ((uint32_t)(row & ~31) << 16), lo);
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
     tc::fence_async_smem();
 }
 
@@ -593,22 +606,21 @@ __device__ __forceinline__ void stage_weights(const MlpDesc &M, const float *Wg,
 // EVAL: 0 one episode per thread, 1 warp-cooperative tiles (both on the FP32 pipe, bit-identical), 2 the hidden layers
 // on the tensor cores (qt_policy_tc.cuh; the block's 128 episodes are one MMA operand, two blocks per SM).
 template <int MOTION, int MINB, int EVAL>
-__global__ void __launch_bounds__(kPolicyThreads, MINB)
+__global__ void __launch_bounds__(EVAL == 2 ? tc::kThreads : kPolicyThreads, MINB)
     rollout_policy_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                           const __grid_constant__ MlpDesc M, const __grid_constant__ PolicyArgs A) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int T = kPolicyThreads;
     constexpr bool TILED = EVAL == 1, TC = EVAL == 2;
-    static_assert(!TC || T == tc::kRows, "the tensor-core evaluation maps one block to one M = 128 operand");
+    constexpr int T = TC ? tc::kThreads : kPolicyThreads;
     const int64_t E = A.E;
     const int64_t e_raw = (int64_t)blockIdx.x * T + threadIdx.x;
     float *tile0 = nullptr, *tile1 = nullptr;
     uint32_t tmem_base = 0u, mma_phase = 0u;
     if constexpr (TC) {
         stage_weights_tc(M, A.W, smem_f);
-        uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_f + tc::kBar + 2);
+        uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_f + tc::kTmemSlot);
         if (threadIdx.x < 32) tc::tmem_alloc(tmem_slot);
-        if (threadIdx.x == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(smem_f + tc::kBar), 1);
+        if (threadIdx.x % tc::kRows == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(smem_f + tc::kBar) + threadIdx.x / tc::kRows, 1);
         tc::fence_async_smem();      // the staged weights are read by the tensor core
         tc::fence_before_sync();
         __syncthreads();
@@ -661,10 +673,10 @@ __global__ void __launch_bounds__(kPolicyThreads, MINB)
     while (true) {
         float feat[QT_FEATURE_DIM];
         if constexpr (TC) {
-            // the block leaves together; the barrier that takes the vote also publishes the feature rows
+            // the 128 episodes of a set leave together; the barrier that takes the vote also publishes the feature rows
             make_features(s, tp, tv, feat);
-            tc_store_features(smem_f, feat);
-            if (!__syncthreads_or(alive)) break;
+            tc_store_features(smem_f, tmem_base, feat);
+            if (!tc::set_sync_or(1 + threadIdx.x / tc::kRows, alive)) break;
         } else if constexpr (TILED) {
             if (!__any_sync(0xffffffffu, alive)) break;
         } else {
@@ -869,11 +881,12 @@ static size_t smem_plan_tiled(const MlpDesc &M) {
 template <int MOTION, int MINB, int EVAL>
 static cudaError_t launch_policy_as(const qt_params &P, const DynConsts &C, const MlpDesc &M, const PolicyArgs &A,
                                     size_t smem, cudaStream_t st) {
-    const int64_t blocks = (A.E + kPolicyThreads - 1) / kPolicyThreads;
+    constexpr int threads = EVAL == 2 ? tc::kThreads : kPolicyThreads;
+    const int64_t blocks = (A.E + threads - 1) / threads;
     cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, MINB, EVAL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_policy_kernel<MOTION, MINB, EVAL><<<(unsigned)blocks, kPolicyThreads, smem, st>>>(P, C, M, A);
+    rollout_policy_kernel<MOTION, MINB, EVAL><<<(unsigned)blocks, threads, smem, st>>>(P, C, M, A);
     return cudaGetLastError();
 }
 
@@ -883,7 +896,7 @@ static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, PolicyArg
     C.init(P);
     too_wide = false;
     if (M.tc_ok && (P.debug_flags & QT_FLAG_POLICY_TENSOR_CORES) && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD))
-        return launch_policy_as<MOTION, 2, 2>(P, C, M, A, (size_t)tc::kFloats * sizeof(float), st);
+        return launch_policy_as<MOTION, 1, 2>(P, C, M, A, (size_t)tc::kFloats * sizeof(float), st);
     if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024) {
         // three resident blocks (168 registers, the env state spills to L1 across the network evaluation)
         // when the shared memory allows, else two or one

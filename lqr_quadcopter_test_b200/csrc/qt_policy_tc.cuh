@@ -1,47 +1,57 @@
 // qt_policy_tc.cuh — the two hidden layers of the deep tracking policy on the 5th-generation tensor cores
 // (controllers/deep_tracking_policy.py:114-147, PolicyNetwork.forward).
 //
-// A block of 128 threads = 128 episodes is one M = 128 operand: episode i is row i of A and lane i of the
-// accumulator in tensor memory.  Per env step and layer:
+// A "set" of 128 threads = 128 episodes is one M = 128 operand: episode i is row i of A and lane i of the
+// accumulator in tensor memory.  A block is kSets independent sets (own mbarrier, own named barrier, own TMEM columns)
+// that share one staged copy of the weights — the weights (44 KB) are what kept a one-set block at two blocks = 8 warps
+// per SM; four sets in one block are 16 warps per SM.  Per env step and layer:
 //   every thread splits its activation row into a TF32 head and tail (x = hi + lo, hi = cvt.rna.tf32(x),
-//   lo = x - hi exactly) and stores both into shared memory in the canonical K-major core-matrix layout
-//   (no swizzle: 8 rows x 16 bytes per core matrix; the 16-byte chunk c of row m lives at (c * 128 + m) * 16, so a
-//   warp's 16-byte stores are consecutive and conflict free);
-//   one thread issues, per k-step of 8, the three `tcgen05.mma.cta_group::1.kind::tf32` of the 3xTF32 scheme
-//   (A_lo B_hi + A_hi B_lo + A_hi B_hi; the weights were split once when the block staged them; fp32 accumulation
-//   in TMEM) and a `tcgen05.commit` onto an mbarrier;
+//   lo = x - hi exactly); the heads go to shared memory in the canonical K-major core-matrix layout (no swizzle:
+//   8 rows x 16 bytes per core matrix; the 16-byte chunk c of row m lives at (c * 128 + m) * 16, so a warp's 16-byte
+//   stores are consecutive and conflict free), the tails to the set's TMEM columns with `tcgen05.st` (the thread's
+//   own lane: no shared memory, which is what makes room for four sets);
+//   one thread of the set issues, per k-step of 8, the three `tcgen05.mma.cta_group::1.kind::tf32` of the 3xTF32
+//   scheme — A_lo[TMEM] B_hi + A_hi[smem] B_lo + A_hi[smem] B_hi; the weights were split once when the block staged
+//   them; fp32 accumulation in TMEM — and a `tcgen05.commit` onto the set's mbarrier;
 //   every thread waits on the mbarrier, reads its own 64 accumulators with `tcgen05.ld.32x32b` (warp w owns TMEM
-//   lanes 32 w .. 32 w + 31), adds the bias and applies the activation.
+//   lanes 32 (w % 4) .. + 31), adds the bias and applies the activation.
 // The 64 -> 4 output layer stays on the FP32 pipe, from registers (256 FMAs per episode: a tensor-core round trip
 // would cost more than it saves, and this keeps torch's order of summation for that layer).
 // Accuracy: dropping lo * lo and the truncation of lo to 11 bits leave a relative error of about 2^-21 per product —
 // the size of fp32 summation-order noise in a 64-term dot product — so this evaluation is NOT bit-identical to the
 // FP32-pipe evaluations (qt_policy.cu), which remain the default and the parity path; the tests bound the difference.
 // Shapes: two hidden layers of at most 64 units (the reference's default 64-64), zero padded to 64.
-// Shared memory per block: A 64 KB (hi + lo, K = 64) + weights 44 KB (18->64 and 64->64, hi + lo) + 2 KB: two
-// blocks per SM.  TMEM: 64 columns per block.
+// Shared memory per block: kSets x 32 KB (A heads, K = 64) + weights 44 KB (18->64 and 64->64, hi + lo) + 2 KB =
+// 174 KB with four sets: one block of 512 threads per SM.  TMEM: 128 columns per set (64 accumulators + 64 tails).
 #pragma once
 #include <stdint.h>
 
 namespace qt {
 namespace tc {
 
-constexpr int kRows = 128;                 // episodes per block = M of the MMA
+#ifndef QT_TC_SETS
+#define QT_TC_SETS 4
+#endif
+constexpr int kSets = QT_TC_SETS;          // independent 128-episode sets per block
+constexpr int kRows = 128;                 // episodes per set = M of the MMA
+constexpr int kThreads = kSets * kRows;
 constexpr int kN = 64;                     // hidden width (padded)
 constexpr int kK0 = 24;                    // 18 features padded to a multiple of the MMA's K = 8
 constexpr int kK1 = 64;
-constexpr int kTmemCols = 64;
+constexpr int kColsPerSet = 128;           // TMEM columns of a set: accumulator [0, 64) | A tails [64, 128)
+constexpr int kTmemCols = kSets * kColsPerSet <= 128 ? 128 : (kSets * kColsPerSet <= 256 ? 256 : 512);
+static_assert(kSets >= 1 && kSets <= 4, "512 TMEM columns hold four sets");
 // float offsets into the block's shared memory
-constexpr int kAHi = 0;                                  // [16 chunks][128 rows][4]
-constexpr int kALo = kAHi + kRows * kK1;
-constexpr int kB0Hi = kALo + kRows * kK1;                // [6 chunks][64 units][4]
+constexpr int kAHi = 0;                                  // [set][16 chunks][128 rows][4]
+constexpr int kB0Hi = kAHi + kSets * kRows * kK1;        // [6 chunks][64 units][4]
 constexpr int kB0Lo = kB0Hi + kN * kK0;
 constexpr int kB1Hi = kB0Lo + kN * kK0;                  // [16 chunks][64 units][4]
 constexpr int kB1Lo = kB1Hi + kN * kK1;
 constexpr int kW3 = kB1Lo + kN * kK1;                    // [64][4] output layer
 constexpr int kBias = kW3 + kN * 4;                      // b1[64] b2[64] b3[4]
-constexpr int kBar = kBias + 2 * kN + 4;                 // mbarrier (8 bytes, 8-byte aligned) + TMEM base address
-constexpr int kFloats = kBar + 4;
+constexpr int kBar = kBias + 2 * kN + 4;                 // kSets mbarriers (8 bytes each, 8-byte aligned)
+constexpr int kTmemSlot = kBar + 2 * kSets;              // TMEM base address written by tcgen05.alloc
+constexpr int kFloats = kTmemSlot + 2;
 static_assert(kBar % 2 == 0, "mbarrier alignment");
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
@@ -67,6 +77,35 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
         : "memory");
+}
+
+// the same with the A operand in tensor memory (row i = lane i, one 32-bit column per K element)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+// named barrier of one set (id 1 + set, 128 threads); the second form also ORs a predicate over the set
+__device__ __forceinline__ void set_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ bool set_sync_or(int id, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %2, 0;\n\t"
+        "bar.red.or.pred p, %1, 128, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(r)
+        : "r"(id), "r"((uint32_t)pred)
+        : "memory");
+    return r != 0u;
 }
 
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
@@ -126,6 +165,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive columns of this thread's TMEM lane from registers (complete after tmem_st_wait)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = __float_as_uint(v[i]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // x = hi + lo with hi the nearest TF32 (ties away) and lo = x - hi exact in fp32 (the MMA reads lo's top 19 bits)
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     uint32_t h;
@@ -134,26 +190,27 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     lo = x - hi;
 }
 
-// store four consecutive K values of this thread's row (chunk c) as head and tail
-__device__ __forceinline__ void store_chunk(float *smem, int row, int c, float x0, float x1, float x2, float x3) {
-    float4 hi, lo;
-    split_tf32(x0, hi.x, lo.x);
-    split_tf32(x1, hi.y, lo.y);
-    split_tf32(x2, hi.z, lo.z);
-    split_tf32(x3, hi.w, lo.w);
-    *reinterpret_cast<float4 *>(smem + kAHi + (c * kRows + row) * 4) = hi;
-    *reinterpret_cast<float4 *>(smem + kALo + (c * kRows + row) * 4) = lo;
+// four consecutive K values of this thread's row (chunk c): heads to the set's A tile in shared memory, tails to lo[]
+__device__ __forceinline__ void store_chunk(float *a_hi, int row, int c, float x0, float x1, float x2, float x3, float *lo) {
+    float4 hi;
+    split_tf32(x0, hi.x, lo[0]);
+    split_tf32(x1, hi.y, lo[1]);
+    split_tf32(x2, hi.z, lo[2]);
+    split_tf32(x3, hi.w, lo[3]);
+    *reinterpret_cast<float4 *>(a_hi + (c * kRows + row) * 4) = hi;
 }
 
-// one layer's MMAs: D[128][64] = A[128][K] B[64][K]', three TF32 products per k-step of 8; thread 0 of the block
-__device__ __forceinline__ void issue_layer(const float *smem, int b_hi, int b_lo, int ksteps, uint32_t d_tmem, uint64_t *bar) {
-    const uint32_t a_hi = smem_u32(smem + kAHi), a_lo = smem_u32(smem + kALo);
+// one layer's MMAs of one set: D[128][64] = A[128][K] B[64][K]', three TF32 products per k-step of 8; one thread
+__device__ __forceinline__ void issue_layer(const float *smem, int set, int b_hi, int b_lo, int ksteps, uint32_t set_tmem,
+                                            uint64_t *bar) {
+    const uint32_t a_hi = smem_u32(smem + kAHi + set * kRows * kK1);
     const uint32_t bh = smem_u32(smem + b_hi), bl = smem_u32(smem + b_lo);
     constexpr uint32_t kALbo = kRows * 16, kBLbo = kN * 16, kSbo = 128;
+    const uint32_t d_tmem = set_tmem, a_lo = set_tmem + 64;
     for (int ks = 0; ks < ksteps; ks++) {
-        const uint64_t dah = smem_desc(a_hi + ks * 2 * kALbo, kALbo, kSbo), dal = smem_desc(a_lo + ks * 2 * kALbo, kALbo, kSbo);
+        const uint64_t dah = smem_desc(a_hi + ks * 2 * kALbo, kALbo, kSbo);
         const uint64_t dbh = smem_desc(bh + ks * 2 * kBLbo, kBLbo, kSbo), dbl = smem_desc(bl + ks * 2 * kBLbo, kBLbo, kSbo);
-        mma_tf32(d_tmem, dal, dbh, ks > 0 ? 1u : 0u);
+        mma_tf32_ts(d_tmem, a_lo + ks * 8, dbh, ks > 0 ? 1u : 0u);
         mma_tf32(d_tmem, dah, dbl, 1u);
         mma_tf32(d_tmem, dah, dbh, 1u);
     }
