@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_
         if (!conv) {
             iters = it + 1;
             if (D2 <= kDareTol * kDareTol * H2) conv = true;
-            if (!(D2 == D2)) {  // NaN: stop, reported through info
+            if (!(D2 == D2) || !(H2 <= 1.79769313486231570e308)) {  // NaN, or H overflowed (inf <= inf would pass the test above): stop, reported through info
                 conv = true;
                 ok = false;
             }

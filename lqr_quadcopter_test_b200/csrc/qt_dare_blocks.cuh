@@ -213,7 +213,7 @@ __device__ __forceinline__ void blk_solve(const double *Ap, const double *Bp, co
             }
         iters = it + 1;
         if (d2 <= tol * tol * h2) conv = true;
-        if (!(d2 == d2)) {  // NaN: stop, reported through info
+        if (!(d2 == d2) || !(h2 <= 1.79769313486231570e308)) {  // NaN, or H overflowed (inf <= inf would pass the test above): stop, reported through info
             conv = true;
             ok = false;
         }
