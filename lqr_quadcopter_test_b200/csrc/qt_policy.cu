@@ -476,32 +476,36 @@ __device__ __forceinline__ void stage_weights_tc(const MlpDesc &M, const float *
 // NEXT_A: store the result as the next layer's A operand (heads to shared memory, tails to the set's TMEM columns);
 // else multiply it into the four output accumulators.
 template <int KIND, bool NEXT_A>
-__device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t taddr, const float *bias, int row, float (&o)[4]) {
+__device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t taddr, const float *bias, int row,
+                                            unsigned long long (&o)[2]) {
+#ifndef QT_TC_EPI
+#define QT_TC_EPI 16   // accumulator columns per tcgen05.ld of the epilogue (16 or 32)
+#endif
+    constexpr int W = QT_TC_EPI;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        float d[32];
-        [[maybe_unused]] float lo[32];
-        tc::tmem_ld32(taddr + half * 32, d);
+    for (int part = 0; part < tc::kN / W; part++) {
+        float d[W];
+        [[maybe_unused]] float lo[W];
+        tc::tmem_ld(taddr + part * W, d);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4 *>(bias + half * 32 + j);
+        for (int j = 0; j < W; j += 4) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + part * W + j);
             const float h0 = activate_t<KIND>(d[j] + b.x), h1 = activate_t<KIND>(d[j + 1] + b.y);
             const float h2 = activate_t<KIND>(d[j + 2] + b.z), h3 = activate_t<KIND>(d[j + 3] + b.w);
             if (NEXT_A) {
-                tc::store_chunk(a_hi, row, (half * 32 + j) >> 2, h0, h1, h2, h3, lo + j);
+                tc::store_chunk(a_hi, row, (part * W + j) >> 2, h0, h1, h2, h3, lo + j);
             } else {
+                // output layer on the FP32 pipe: o[0] = (out0, out1), o[1] = (out2, out3) as FFMA2 pairs, ascending k
                 const float h[4] = {h0, h1, h2, h3};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const float4 w = *reinterpret_cast<const float4 *>(smem + tc::kW3 + (half * 32 + j + q) * 4);
-                    o[0] = fmaf(h[q], w.x, o[0]);
-                    o[1] = fmaf(h[q], w.y, o[1]);
-                    o[2] = fmaf(h[q], w.z, o[2]);
-                    o[3] = fmaf(h[q], w.w, o[3]);
+                    const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(smem + tc::kW3 + (part * W + j + q) * 4);
+                    ffma2(h[q], w.x, o[0]);
+                    ffma2(h[q], w.y, o[1]);
                 }
             }
         }
-        if (NEXT_A) tc::tmem_st32(taddr + 64 + half * 32, lo);
+        if constexpr (NEXT_A) tc::tmem_st(taddr + 64 + part * W, lo);
     }
     if (NEXT_A) tc::tmem_st_wait();
 }
@@ -516,7 +520,7 @@ __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *sme
     float *a_hi = smem + tc::kAHi + set * tc::kRows * tc::kK1;
     const uint32_t set_tmem = tmem_base + set * tc::kColsPerSet;
     const uint32_t taddr = set_tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
-    float o[4];
+    unsigned long long o[2] = {0ull, 0ull};
     if (row == 0) {
         tc::fence_after_sync();
         tc::issue_layer(smem, set, tc::kB0Hi, tc::kB0Lo, tc::kK0 / 8, set_tmem, bar);
@@ -536,17 +540,18 @@ __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *sme
     phase ^= 1u;
     tc::fence_after_sync();
     {
-        const float4 b = *reinterpret_cast<const float4 *>(smem + tc::kBias + 2 * tc::kN);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(smem + tc::kBias + 2 * tc::kN);
         o[0] = b.x;
         o[1] = b.y;
-        o[2] = b.z;
-        o[3] = b.w;
     }
     tc_epilogue<KIND, false>(smem, a_hi, taddr, smem + tc::kBias + tc::kN, row, o);
     tc::fence_before_sync();
+    float of[4];
+    unpack2(o[0], of[0], of[1]);
+    unpack2(o[1], of[2], of[3]);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float sg = 1.0f / (1.0f + expf(-o[i]));  // torch.sigmoid
+        const float sg = 1.0f / (1.0f + expf(-of[i]));  // torch.sigmoid
         out[i] = fmaf(sg, M.out_scale[i], M.out_lo[i]);
     }
 }
@@ -574,7 +579,7 @@ __device__ __forceinline__ void tc_store_features(float *smem, uint32_t tmem_bas
     tc::store_chunk(a_hi, row, 3, f[12], f[13], f[14], f[15], lo + 12);
     tc::store_chunk(a_hi, row, 4, f[16], f[17], 0.0f, 0.0f, lo + 16);
     *reinterpret_cast<float4 *>(a_hi + (5 * tc::kRows + row) * 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    tc::tmem_st32(tmem_base + set * tc::kColsPerSet + 64 + ((uint32_t)(row & ~31) << 16), lo);
+    tc::tmem_st(tmem_base + set * tc::kColsPerSet + 64 + ((uint32_t)(row & ~31) << 16), lo);
     tc::tmem_st_wait();
     tc::fence_before_sync();
     tc::fence_async_smem();

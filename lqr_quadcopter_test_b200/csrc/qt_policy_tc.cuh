@@ -148,7 +148,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base) {      // the same w
 }
 
 // 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -166,7 +166,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // 32 consecutive columns of this thread's TMEM lane from registers (complete after tmem_st_wait)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[32]) {
     uint32_t r[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) r[i] = __float_as_uint(v[i]);
@@ -181,6 +181,32 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16-column forms (the epilogues work on quarters of a row: fewer live registers next to the fp64 env state)
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[16]) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __float_as_uint(v[i]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 
 // x = hi + lo with hi the nearest TF32 (ties away) and lo = x - hi exact in fp32 (the MMA reads lo's top 19 bits)
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
