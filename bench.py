@@ -685,32 +685,65 @@ def run_gpu_arm(args) -> None:
 
         torch.manual_seed(0)
         pol = DeepTrackingPolicy(config={"hidden_sizes": [64, 64], "activation": "relu"})
-        # whole waves of the policy kernel's grid: 3 resident blocks of 128 episodes per SM, 4 waves (227 328 on a B200)
-        Ep = min(E, ctx_sm_count(ctx) * 3 * 128 * 4)
+        # whole waves of both policy kernels' grids: 3 resident blocks of 128 episodes (FP32-pipe tiles) and 1 block
+        # of 512 (tensor cores) per SM: multiples of 1536 per SM, 3 waves / 9 waves (227 328 episodes on a B200)
+        Ep = min(E, ctx_sm_count(ctx) * 1536)
         pseeds = torch.arange(Ep, dtype=torch.int64, device=dev) + 42
-        for _ in range(2):
-            rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
-        torch.cuda.synchronize()
-        pev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        pev[0].record()
-        for i in range(5):
-            pout = rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
-            pev[i + 1].record()
-        torch.cuda.synchronize()
-        p_ms = statistics.median(pev[i].elapsed_time(pev[i + 1]) for i in range(5))   # secondary figure: median of five
+
+        def time_policy():
+            for _ in range(2):
+                rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx)
+            torch.cuda.synchronize()
+            pev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            pev[0].record()
+            for i in range(5):
+                out = rollout_device(pol, env, SuccessCriteria(), pseeds, supervisor=ctrl, dataset_stride=10, ctx=ctx,
+                                     want_final_state=True)
+                pev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = statistics.median(pev[i].elapsed_time(pev[i + 1]) for i in range(5))   # secondary figure: median of five
+            return ms, out
+
+        p_ms, pout = time_policy()                      # default: FP32 pipe (FFMA2 tiles), the parity path
+        pol.tensor_cores = True
+        t_ms, tout = time_policy()                      # hidden layers on the tensor cores (tcgen05, 3xTF32)
+        pol.tensor_cores = False
         p_steps = float(pout["metrics"][0].sum().item())
+        t_steps = float(tout["metrics"][0].sum().item())
         fma_per_step = 18 * 64 + 64 * 64 + 64 * 4
         fp32_nominal = ctx_sm_count(ctx) * 128 * 2 * (clock_info.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
         fp32_peak, _ = ctx.fp32_peak_probe(1 << 17)        # measured: register-resident FFMA chains, this run
+        on_diff = (pout["metrics"][3] - tout["metrics"][3]).abs()
+        # the two evaluations on the same 40 steps (the random network's episodes leave the box and diverge chaotically
+        # over 30 s, so full-length final states say nothing; tests/test_parity_gpu.py bounds this figure at 1e-5)
+        short = {}
+        for flag in (False, True):
+            pol.tensor_cores = flag
+            short[flag] = rollout_device(pol, env, SuccessCriteria(), pseeds[:65536], max_steps=40, ctx=ctx,
+                                         want_final_state=True)["final_state"]
+        pol.tensor_cores = False
+        short_diff = float((short[False] - short[True]).abs().max().item())
         policy = {"metric": "closed-loop env-steps/s with the 64-64 deep tracking policy acting (fp32, in-kernel)",
                   "value": p_steps / (p_ms * 1e-3), "unit": "env-steps/s", "episodes": Ep, "ms_per_launch": p_ms,
+                  "path": "FP32 pipe (warp-cooperative FFMA2 tiles; bit-identical to a sequential fp32 evaluation; default)",
                   "includes": "reset + rollout + supervisor labels and 18+4 fp32 data-set rows every 10th step",
                   "roofline": {"bound": "fp32", "achieved": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12,
                                "peak": fp32_peak, "unit": "TFLOP/s",
                                "frac": p_steps * fma_per_step * 2 / (p_ms * 1e-3) / 1e12 / fp32_peak,
                                "peak_source": "register-resident FFMA probe (qt_fp32_peak_probe) in this run",
                                "nominal_peak": fp32_nominal,
-                               "algorithmic_flops_per_env_step": 2 * fma_per_step}}
+                               "algorithmic_flops_per_env_step": 2 * fma_per_step},
+                  "tensor_cores": {
+                      "path": "hidden layers as tcgen05.mma kind::tf32 (3xTF32 split, fp32 accumulation in TMEM), output layer "
+                              "on the FP32 pipe; DeepTrackingPolicy(config={'tensor_cores': True}) / QT_FLAG_POLICY_TENSOR_CORES",
+                      "value": t_steps / (t_ms * 1e-3), "unit": "env-steps/s", "ms_per_launch": t_ms,
+                      "speedup_over_fp32_pipe": (t_steps / t_ms) / (p_steps / p_ms),
+                      "fp32_equivalent_tflops": t_steps * fma_per_step * 2 / (t_ms * 1e-3) / 1e12,
+                      "tf32_mma_tflops_issued": t_steps * 3 * 2 * (24 * 64 + 64 * 64) / (t_ms * 1e-3) / 1e12,
+                      "vs_fp32_pipe": {"max_abs_state_diff_after_40_steps": short_diff,
+                                       "success_flags_differing": int((pout["metrics"][11] != tout["metrics"][11]).sum().item()),
+                                       "on_target_counts_differing": int((on_diff > 0).sum().item()),
+                                       "max_on_target_count_diff": int(on_diff.max().item()), "episodes": Ep}}}
     except Exception as exc:  # the headline line must not be lost to the secondary section
         policy = {"error": repr(exc)}
 

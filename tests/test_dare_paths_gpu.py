@@ -205,3 +205,30 @@ def test_failure_behaviour_follows_scipy(gpu_ctx):
             solve_discrete_are(A2, B2, np.eye(2), np.eye(1))
         for (_, _, _, info) in _both(gpu_ctx, A2, B2, np.eye(2)[None], np.eye(1)[None]):
             assert info[0] != 0
+
+
+def test_validation_thresholds_follow_numpy_on_dense_weights(gpu_ctx):
+    """Q / R validation (riccati_lqr.py:57-116) for DENSE symmetric weights whose smallest eigenvalue sits on either
+    side of the reference's thresholds (Q >= -1e-10, R > 1e-10): the kernel's LDL' certificate with its eigenvalue
+    fallback must take numpy's decision in every case."""
+    rng = np.random.default_rng(5)
+    n, m = 6, 4
+    A, B = _design(n)
+    q_mins = [-3e-10, -1.3e-10, -1.1e-10, -0.9e-10, -0.7e-10, -0.3e-10, 0.0, 1e-11, 1e-6, 0.5]
+    r_mins = [-1e-3, 0.0, 0.5e-10, 0.9e-10, 1.1e-10, 1.3e-10, 1.7e-10, 3e-10, 1e-6, 0.5]
+    Qs, Rs, expect = [], [], []
+    for qm in q_mins:
+        for rm in r_mins:
+            Vq, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            Vr, _ = np.linalg.qr(rng.standard_normal((m, m)))
+            Q = (Vq * np.concatenate([[qm], rng.uniform(0.1, 2.0, n - 1)])) @ Vq.T
+            R = (Vr * np.concatenate([[rm], rng.uniform(0.5, 2.0, m - 1)])) @ Vr.T
+            Q, R = (Q + Q.T) / 2, (R + R.T) / 2
+            ok = (not np.any(np.linalg.eigvalsh(Q) < -1e-10)) and (not np.any(np.linalg.eigvalsh(R) <= 1e-10))
+            Qs.append(Q), Rs.append(R), expect.append(ok)
+    (_, _, _, i0), (_, _, _, i1) = _both(gpu_ctx, A, B, np.array(Qs), np.array(Rs))
+    got = i0 != 3
+    assert (i0 == 3).tolist() == (i1 == 3).tolist()
+    wrong = [(q_mins[k // len(r_mins)], r_mins[k % len(r_mins)]) for k in range(len(expect)) if got[k] != expect[k]]
+    assert not wrong, f"validation differs from numpy for (lambda_min(Q), lambda_min(R)) = {wrong}"
+    assert sum(expect) >= 30 and sum(expect) <= 70
