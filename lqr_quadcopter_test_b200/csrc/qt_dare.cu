@@ -339,16 +339,16 @@ __device__ __forceinline__ void store_rows(double *M, int row0, const double (&x
     for (int r = 0; r < R; r++) store_row<N>(M, row0 + r, x[r]);
 }
 
+// The systems [blk * per_block, (blk + 1) * per_block) of the batch, by one thread block.
 template <int N, int R>
-__global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_BLOCKS)
-    dare_kernel(const __grid_constant__ DareArgs D) {
+__device__ __forceinline__ void dare_block(const DareArgs &D, int64_t blk) {
     extern __shared__ __align__(16) double smem[];
     using L = Lay<N, R>;
     constexpr int LD = L::LD, TEAM = L::TEAM, WARPS = DareCfg<N, R>::WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int team = lane / TEAM, li = lane % TEAM, team_base = lane - li;
     const int row0 = li * R;  // first matrix row held by this lane
-    const int64_t sys = ((int64_t)blockIdx.x * WARPS + warp) * L::TEAMS + team;
+    const int64_t sys = (blk * WARPS + warp) * L::TEAMS + team;
     const int n = D.n, m = D.m;
     bool ghost = (team >= L::TEAMS) || (sys >= D.batch);
     // only systems the validation kernel passed on: rejected ones (info = 3) and the ones the decoupled path has
@@ -575,6 +575,19 @@ __global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_
     }
 }
 
+// Grid-stride over the batch's blocks of systems.  With the decoupled path in front (qt_dare_blocks.cuh) nearly every
+// block finds nothing marked for it: a grid of a few blocks per SM that walks the batch replaces tens of thousands of
+// 96 KB blocks that start only to exit (85 us of a 1.5 ms launch for 2^20 n = 9 systems).  The dense-only path keeps
+// one block per group (grid = number of groups), which lets the hardware balance systems of different iteration counts.
+template <int N, int R>
+__global__ void __launch_bounds__(DareCfg<N, R>::WARPS * 32, DareCfg<N, R>::MIN_BLOCKS)
+    dare_kernel(const __grid_constant__ DareArgs D, int64_t n_blocks) {
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        dare_block<N, R>(D, blk);
+        __syncthreads();   // the next group reuses the shared-memory matrices
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Validation (riccati_lqr.py:57-116): Q symmetric (np.allclose atol 1e-8, rtol 1e-5) with
 // eigenvalues >= -1e-10, R symmetric with eigenvalues > 1e-10.  One thread per system.  Exactly
@@ -694,7 +707,7 @@ __global__ void dare_validate_kernel(const __grid_constant__ DareArgs D, int onl
 }
 
 template <int N, int R>
-static cudaError_t launch_dare(const DareArgs &D, cudaStream_t st) {
+static cudaError_t launch_dare(const DareArgs &D, cudaStream_t st, int64_t max_grid) {
     using L = Lay<N, R>;
     constexpr int WARPS = DareCfg<N, R>::WARPS;
     const size_t smem = (size_t)WARPS * L::SLOTS * L::BLOCK * sizeof(double);
@@ -702,7 +715,8 @@ static cudaError_t launch_dare(const DareArgs &D, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const int64_t per_block = (int64_t)WARPS * L::TEAMS;
     const int64_t blocks = (D.batch + per_block - 1) / per_block;
-    dare_kernel<N, R><<<(unsigned)blocks, WARPS * 32, smem, st>>>(D);
+    const int64_t grid = (max_grid > 0 && blocks > max_grid) ? max_grid : blocks;
+    dare_kernel<N, R><<<(unsigned)grid, WARPS * 32, smem, st>>>(D, blocks);
     return cudaGetLastError();
 }
 
@@ -772,11 +786,14 @@ extern "C" int qt_dare_batched(qt_context *ctx, int32_t n, int32_t m, int64_t ba
     if (rc) return rc;
     const int need = n > m ? n : m;
     // <padded size N, rows per lane R>: lanes per system N / R, systems per warp 32 / (N / R)
-    if (need <= 4) err = launch_dare<4, 2>(D, ctx->stream);          // 2 lanes, 16 systems per warp
-    else if (need <= 6) err = launch_dare<6, QT_DARE_R6>(D, ctx->stream);
-    else if (need <= 9) err = launch_dare<QT_DARE_N9, QT_DARE_R9>(D, ctx->stream);
-    else if (need <= 12) err = launch_dare<12, QT_DARE_R12>(D, ctx->stream);
-    else err = launch_dare<16, QT_DARE_R16>(D, ctx->stream);
+    // after the decoupled path most groups of systems have nothing left for the dense kernel: a few blocks per SM walk
+    // the batch (grid-stride) instead of one block per group
+    const int64_t max_grid = try_blocks ? (int64_t)ctx->sm_count * 4 : 0;
+    if (need <= 4) err = launch_dare<4, 2>(D, ctx->stream, max_grid);          // 2 lanes, 16 systems per warp
+    else if (need <= 6) err = launch_dare<6, QT_DARE_R6>(D, ctx->stream, max_grid);
+    else if (need <= 9) err = launch_dare<QT_DARE_N9, QT_DARE_R9>(D, ctx->stream, max_grid);
+    else if (need <= 12) err = launch_dare<12, QT_DARE_R12>(D, ctx->stream, max_grid);
+    else err = launch_dare<16, QT_DARE_R16>(D, ctx->stream, max_grid);
     if (err != cudaSuccess) return fail(ctx, QT_ERR_CUDA, "dare_kernel launch", cudaGetErrorString(err));
     ctx->launches += 1;
     return QT_OK;
