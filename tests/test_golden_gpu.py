@@ -346,6 +346,13 @@ def test_policy_network_matches_reference(golden, gb, name):
         out = gb.rollout_policy(P.make_params(env), g[key + "_state0"], g[key + "_tparams"], pol,
                                 max_steps=int(g[key + "_max_steps"]), traj_stride=250)
         gc.assert_policy_rollout_matches(np, out, g, key)
+        # the tensor-core evaluation (two hidden layers of at most 64 units; other shapes ignore the flag and stay on
+        # the FP32 pipe) is held to the same reference fixture with the same tolerances
+        tcp = P.make_params(env)
+        tcp.debug_flags = P.FLAG_POLICY_TENSOR_CORES
+        out_tc = gb.rollout_policy(tcp, g[key + "_state0"], g[key + "_tparams"], pol,
+                                   max_steps=int(g[key + "_max_steps"]), traj_stride=250)
+        gc.assert_policy_rollout_matches(np, out_tc, g, key)
 
 
 @pytest.mark.parametrize("sup", ["riccati", "pid"])

@@ -140,11 +140,14 @@ def test_sweep_candidates_against_the_oracle(gb, orc):
     assert int(np.argmax(sc_got[0])) == int(np.argmax(sc_ref[0]))
 
 
-@pytest.mark.parametrize("motion", ["stationary", "circular"])
-def test_policy_episodes_against_the_oracle(golden, gb, orc, motion):
-    """§8(f).2: the tiled fp32 policy kernel (64-64 network fitted to the LQR law) against the oracle's fp32 C network
-    over full episodes.  fp32 dot products in a different order move the state by ~1e-5 m, so single samples near the
-    0.5 m radius flip: those episodes are counted, printed and bounded; flags and hard counters must be identical."""
+@pytest.mark.parametrize("motion,tensor_cores", [("stationary", False), ("circular", False), ("stationary", True),
+                                                 ("circular", True)])
+def test_policy_episodes_against_the_oracle(golden, gb, orc, motion, tensor_cores):
+    """§8(f).2: the policy kernel (64-64 network fitted to the LQR law) against the oracle's fp32 C network over full
+    episodes — the tiled FP32-pipe evaluation, and the tensor-core evaluation (QT_FLAG_POLICY_TENSOR_CORES: tcgen05
+    TF32 MMAs with the 3xTF32 split), held to the SAME bounds.  fp32 dot products in a different order move the state by
+    ~1e-5 m, so single samples near the 0.5 m radius flip: those episodes are counted, printed and bounded; flags and
+    hard counters must be identical."""
     E = max(8192, E_SOAK // 2)
     g = golden["policy"]
     name = "relu_64_64"
@@ -155,6 +158,9 @@ def test_policy_episodes_against_the_oracle(golden, gb, orc, motion):
     prm = P.make_params(env, gc.controller_ns())
     s0, tp = orc.reset_reference(prm, np.arange(10_000, 10_000 + E))
     ref = orc.rollout_policy(prm, s0, tp, om, max_steps=3002, n_threads=os.cpu_count() or 8)
+    if tensor_cores:
+        prm.debug_flags = P.FLAG_POLICY_TENSOR_CORES
+        name = name + " on the tensor cores"
     got = gb.rollout_policy(prm, s0, tp, pol, max_steps=3002)
     M, G = got["metrics"], ref["metrics"]
     per_ep = np.abs(got["final_state"] - ref["final_state"]).max(axis=0)
