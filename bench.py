@@ -628,7 +628,16 @@ def run_gpu_arm(args) -> None:
     same = bool(torch.equal(metrics_host, metrics.cpu()))
 
     # ---- collective secondary sections (every rank takes part; times are max over ranks) ---------------
-    fp64_tflops, _ = ctx.fp64_peak_probe(1 << 17)
+    # the FP64 roofline denominator with a clock record of its own: the probe repeated under the clock sampler (the first
+    # repetitions give nvidia-smi time to come up under the same load)
+    with ClockSampler(local) as probe_clocks:
+        for _ in range(20):
+            ctx.fp64_peak_probe(1 << 17)
+        probe_clocks.mark_start()
+        probe_vals = [ctx.fp64_peak_probe(1 << 17)[0] for _ in range(20)]
+        probe_clocks.mark_end()
+    fp64_tflops = statistics.median(probe_vals)
+    probe_clock_info = probe_clocks.summary()
     dare_section = run_dare_section(ctx, rank, world, fp64_tflops, barrier)
     strong = run_strong_section(ctx, rank, world, barrier, args)
 
@@ -664,7 +673,8 @@ def run_gpu_arm(args) -> None:
         "bound": "fp64", "kernel": "rollout_kernel<linear, LQR, lean>" + (" structured loop" if structured else " general loop"),
         "achieved": achieved, "peak": fp64_tflops,
         "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops > 0 else None, "traffic": traffic,
-        "peak_source": "register-resident DFMA probe (qt_fp64_peak_probe) in this run; MEASURED_PEAKS.json has no FP64 entry",
+        "peak_source": "register-resident DFMA probe (qt_fp64_peak_probe) in this run, median of 20; MEASURED_PEAKS.json has no FP64 entry",
+        "peak_clocks": probe_clock_info, "peak_spread": [min(probe_vals), max(probe_vals)],
         "algorithmic_flops_per_env_step": flops_step, "dense_flops_per_env_step": FLOPS_PER_ENV_STEP,
         "dense_equivalent_tflops": dense_equiv,
         "note": "achieved counts only the flops the executed path needs (324 of the dense 440: products with the "
