@@ -70,8 +70,8 @@ enum qt_controller { QT_CTRL_RICCATI = 0, QT_CTRL_PID = 1 };
 /* QT_DEBUG_POLICY_PER_THREAD: qt_rollout_policy evaluates the network one episode per thread even where
  * the warp-cooperative tiled evaluation applies; results must not change (tests).                   */
 #define QT_DEBUG_POLICY_PER_THREAD 2
-/* QT_FLAG_POLICY_TENSOR_CORES (ABI v6): qt_rollout_policy evaluates the two hidden layers of a network with two
- * hidden layers of at most 64 units (the reference's default 64-64) on the tensor cores — tcgen05.mma kind::tf32 with
+/* QT_FLAG_POLICY_TENSOR_CORES (ABI v6): qt_rollout_policy evaluates the hidden layers of a network with one to three
+ * hidden layers of at most 64 units each (the reference's default 64-64, its "fast" 32-32) on the tensor cores — tcgen05.mma kind::tf32 with
  * the 3xTF32 split (x = hi + lo), fp32 accumulation in tensor memory; the output layer stays on the FP32 pipe.  The
  * result differs from the FP32-pipe evaluation by about 2^-21 relative per product, the size of fp32 summation-order
  * noise; the default (flag clear) is the FP32-pipe evaluation, which the parity fixtures are held to bit for bit.  */

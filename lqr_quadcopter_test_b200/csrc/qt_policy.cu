@@ -53,7 +53,8 @@ struct MlpDesc {
     int t_total;                     // floats of the staged weights
     int t_buf[2];                    // rows (of 32 floats) of the two per-warp activation buffers
     int t_inplace;                   // every hidden layer is one 64-unit column tile: the layers run in place in buffer 0
-    int tc_ok;                       // two hidden layers of at most 64 units: the tensor-core evaluation applies (qt_policy_tc.cuh)
+    int tc_ok;                       // one to three hidden layers of at most 64 units: the tensor-core evaluation applies
+    tc::TcLayout tc;                 // its shared-memory plan (qt_policy_tc.cuh)
 };
 
 static bool describe(const qt_mlp &m, MlpDesc &d) {
@@ -102,7 +103,26 @@ static bool describe(const qt_mlp &m, MlpDesc &d) {
     d.t_buf[0] += 2;     // tile_layer's operand prefetch runs two rows past the layer's input
     if (d.t_buf[1]) d.t_buf[1] += 2;
     d.tiled = m.n_layers >= 2 && fma_tiled * 4 <= fma_packed * 5;   // at most 25 % padding work
-    d.tc_ok = m.n_layers == 3 && m.dims[1] <= tc::kN && m.dims[2] <= tc::kN;
+    d.tc_ok = m.n_layers >= 2 && m.n_layers - 1 <= tc::kMaxHidden;
+    for (int l = 1; l < m.n_layers; l++) d.tc_ok = d.tc_ok && m.dims[l] <= tc::kN;
+    if (d.tc_ok) {
+        tc::TcLayout &t = d.tc;
+        t.hidden = m.n_layers - 1;
+        int at = tc::kWeights;
+        for (int l = 0; l < t.hidden; l++) {
+            t.n[l] = (m.dims[l + 1] + 15) & ~15;
+            t.k[l] = l == 0 ? tc::kK0 : t.n[l - 1];
+            t.b_hi[l] = at;
+            t.b_lo[l] = at + t.k[l] * t.n[l];
+            at += 2 * t.k[l] * t.n[l];
+        }
+        t.w3 = at;
+        t.bias = t.w3 + tc::kN * 4;
+        t.bar = t.bias + tc::kMaxHidden * tc::kN + 4;
+        t.bar += t.bar & 1;                      // 8-byte alignment of the mbarriers
+        t.tmem_slot = t.bar + 2 * tc::kSets;
+        t.floats = t.tmem_slot + 2;
+    }
     return true;
 }
 
@@ -442,48 +462,50 @@ __device__ __forceinline__ void make_features(const double (&s)[12], const doubl
 }
 
 // ---- tensor-core evaluation (qt_policy_tc.cuh) ------------------------------------------------------
-// Stage the packed weights for the tensor-core evaluation: both hidden layers as B operands (unit n, input k) in the
+// Stage the packed weights for the tensor-core evaluation: the hidden layers as B operands (unit n, input k) in the
 // canonical K-major layout, split into TF32 head and tail; the output layer and the biases as plain fp32.
 __device__ __forceinline__ void stage_weights_tc(const MlpDesc &M, const float *__restrict__ Wg, float *smem) {
-    for (int l = 0; l < 2; l++) {
-        const int K = l == 0 ? tc::kK0 : tc::kK1, rows = M.rows[l], outp = M.outp[l];
+    const tc::TcLayout &t = M.tc;
+    for (int l = 0; l < t.hidden; l++) {
+        const int K = t.k[l], N = t.n[l], rows = M.rows[l], outp = M.outp[l];
         const float *src = Wg + M.w_off[l];
-        float *hi = smem + (l == 0 ? tc::kB0Hi : tc::kB1Hi), *lo = smem + (l == 0 ? tc::kB0Lo : tc::kB1Lo);
-        for (int i = threadIdx.x; i < K * tc::kN; i += blockDim.x) {
-            const int k = i / tc::kN, n = i - k * tc::kN;
+        float *hi = smem + t.b_hi[l], *lo = smem + t.b_lo[l];
+        for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+            const int k = i / N, n = i - k * N;
             const float w = (k < rows && n < outp) ? src[k * outp + n] : 0.0f;
-            float h, t;
-            tc::split_tf32(w, h, t);
-            const int at = ((k >> 2) * tc::kN + n) * 4 + (k & 3);
+            float h, tl;
+            tc::split_tf32(w, h, tl);
+            const int at = ((k >> 2) * N + n) * 4 + (k & 3);
             hi[at] = h;
-            lo[at] = t;
+            lo[at] = tl;
         }
         for (int n = threadIdx.x; n < tc::kN; n += blockDim.x)
-            smem[tc::kBias + l * tc::kN + n] = n < outp ? src[rows * outp + n] : 0.0f;
+            smem[t.bias + l * tc::kN + n] = n < outp ? src[rows * outp + n] : 0.0f;
     }
     {
-        const int rows = M.rows[2], outp = M.outp[2];   // outp = 4
-        const float *src = Wg + M.w_off[2];
+        const int L = t.hidden, rows = M.rows[L], outp = M.outp[L];   // outp = 4
+        const float *src = Wg + M.w_off[L];
         for (int i = threadIdx.x; i < tc::kN * 4; i += blockDim.x) {
             const int k = i >> 2, j = i & 3;
-            smem[tc::kW3 + i] = k < rows ? src[k * outp + j] : 0.0f;
+            smem[t.w3 + i] = k < rows ? src[k * outp + j] : 0.0f;
         }
-        if (threadIdx.x < 4) smem[tc::kBias + 2 * tc::kN + threadIdx.x] = src[rows * outp + threadIdx.x];
+        if (threadIdx.x < 4) smem[t.bias + tc::kMaxHidden * tc::kN + threadIdx.x] = src[rows * outp + threadIdx.x];
     }
 }
 
-// Second half of a hidden layer on the tensor cores: read this thread's 64 accumulators, add the bias, activate.
+// Second half of a hidden layer on the tensor cores: read this thread's n accumulators, add the bias, activate.
 // NEXT_A: store the result as the next layer's A operand (heads to shared memory, tails to the set's TMEM columns);
 // else multiply it into the four output accumulators.
-template <int KIND, bool NEXT_A>
-__device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t taddr, const float *bias, int row,
+// NFIX: the layer's width when it is known at compile time (the 64-64 default: fully unrolled), 0 = run time.
+template <int KIND, bool NEXT_A, int NFIX>
+__device__ __forceinline__ void tc_epilogue(const float *w3, float *a_hi, uint32_t taddr, const float *bias, int n_rt, int row,
                                             unsigned long long (&o)[2]) {
-#ifndef QT_TC_EPI
-#define QT_TC_EPI 16   // accumulator columns per tcgen05.ld of the epilogue (16 or 32)
-#endif
-    constexpr int W = QT_TC_EPI;
+    constexpr int W = 16;   // accumulator columns per tcgen05.ld: quarters of a 64-wide row keep the live registers
+                            // next to the fp64 env state low (32 columns at a time measured 6 % slower)
+    const int n = NFIX ? NFIX : n_rt;
 #pragma unroll
-    for (int part = 0; part < tc::kN / W; part++) {
+    for (int part = 0; part < (NFIX ? NFIX / W : tc::kN / W); part++) {
+        if (!NFIX && part * W >= n) break;
         float d[W];
         [[maybe_unused]] float lo[W];
         tc::tmem_ld(taddr + part * W, d);
@@ -499,7 +521,7 @@ __device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t t
                 const float h[4] = {h0, h1, h2, h3};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(smem + tc::kW3 + (part * W + j + q) * 4);
+                    const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(w3 + (part * W + j + q) * 4);
                     ffma2(h[q], w.x, o[0]);
                     ffma2(h[q], w.y, o[1]);
                 }
@@ -512,40 +534,46 @@ __device__ __forceinline__ void tc_epilogue(float *smem, float *a_hi, uint32_t t
 
 // PolicyNetwork.forward for the 128 episodes of a set; every thread of the set must call it after having stored its
 // feature row with tc_store_features and passed the set barrier that follows.
-template <int KIND>
+// FIX64x2: the reference's default shape, two hidden layers of 64 units — layer count and widths are compile-time
+// constants (the run-time loops of the general form cost 7 % on that shape).
+template <int KIND, bool FIX64x2>
 __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *smem, uint32_t tmem_base, uint32_t &phase,
                                                     float (&out)[4]) {
+    const tc::TcLayout &t = M.tc;
+    constexpr int NF = FIX64x2 ? 64 : 0;
+    const int hidden = FIX64x2 ? 2 : t.hidden;
     const int set = threadIdx.x / tc::kRows, row = threadIdx.x % tc::kRows;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + tc::kBar) + set;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + t.bar) + set;
     float *a_hi = smem + tc::kAHi + set * tc::kRows * tc::kK1;
     const uint32_t set_tmem = tmem_base + set * tc::kColsPerSet;
     const uint32_t taddr = set_tmem + ((uint32_t)(row & ~31) << 16);   // this warp's 32 TMEM lanes
-    unsigned long long o[2] = {0ull, 0ull};
-    if (row == 0) {
-        tc::fence_after_sync();
-        tc::issue_layer(smem, set, tc::kB0Hi, tc::kB0Lo, tc::kK0 / 8, set_tmem, bar);
-    }
-    tc::mbar_wait(bar, phase);
-    phase ^= 1u;
-    tc::fence_after_sync();
-    tc_epilogue<KIND, true>(smem, a_hi, taddr, smem + tc::kBias, row, o);
-    tc::fence_before_sync();     // this thread's tcgen05.ld / st are done before the next MMAs touch those columns
-    tc::fence_async_smem();      // ... and its new A heads are visible to the tensor core
-    tc::set_sync(1 + set);
-    if (row == 0) {
-        tc::fence_after_sync();
-        tc::issue_layer(smem, set, tc::kB1Hi, tc::kB1Lo, tc::kK1 / 8, set_tmem, bar);
-    }
-    tc::mbar_wait(bar, phase);
-    phase ^= 1u;
-    tc::fence_after_sync();
+    unsigned long long o[2];
     {
-        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(smem + tc::kBias + 2 * tc::kN);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(smem + t.bias + tc::kMaxHidden * tc::kN);
         o[0] = b.x;
         o[1] = b.y;
     }
-    tc_epilogue<KIND, false>(smem, a_hi, taddr, smem + tc::kBias + tc::kN, row, o);
-    tc::fence_before_sync();
+#pragma unroll
+    for (int l = 0; l < (FIX64x2 ? 2 : tc::kMaxHidden); l++) {
+        if (!FIX64x2 && l >= hidden) break;
+        if (row == 0) {
+            tc::fence_after_sync();
+            tc::issue_layer(smem, set, t.b_hi[l], t.b_lo[l], FIX64x2 ? 64 : t.n[l], FIX64x2 ? (l == 0 ? tc::kK0 / 8 : 8) : t.k[l] / 8,
+                            set_tmem, bar);
+        }
+        tc::mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+        if (l + 1 < hidden) {
+            tc_epilogue<KIND, true, NF>(smem + t.w3, a_hi, taddr, smem + t.bias + l * tc::kN, t.n[l], row, o);
+            tc::fence_before_sync();     // this thread's tcgen05.ld / st are done before the next MMAs touch those columns
+            tc::fence_async_smem();      // ... and its new A heads are visible to the tensor core
+            tc::set_sync(1 + set);
+        } else {
+            tc_epilogue<KIND, false, NF>(smem + t.w3, a_hi, taddr, smem + t.bias + l * tc::kN, t.n[l], row, o);
+            tc::fence_before_sync();
+        }
+    }
     float of[4];
     unpack2(o[0], of[0], of[1]);
     unpack2(o[1], of[2], of[3]);
@@ -556,13 +584,14 @@ __device__ __forceinline__ void mlp_forward_tc_kind(const MlpDesc &M, float *sme
     }
 }
 
+template <bool FIX64x2>
 __device__ __forceinline__ void mlp_forward_tc(const MlpDesc &M, float *smem, uint32_t tmem_base, uint32_t &phase,
                                                float (&out)[4]) {
     switch (M.activation) {
-    case QT_ACT_TANH: mlp_forward_tc_kind<QT_ACT_TANH>(M, smem, tmem_base, phase, out); break;
-    case QT_ACT_ELU: mlp_forward_tc_kind<QT_ACT_ELU>(M, smem, tmem_base, phase, out); break;
-    case QT_ACT_LEAKY_RELU: mlp_forward_tc_kind<QT_ACT_LEAKY_RELU>(M, smem, tmem_base, phase, out); break;
-    default: mlp_forward_tc_kind<QT_ACT_RELU>(M, smem, tmem_base, phase, out); break;
+    case QT_ACT_TANH: mlp_forward_tc_kind<QT_ACT_TANH, FIX64x2>(M, smem, tmem_base, phase, out); break;
+    case QT_ACT_ELU: mlp_forward_tc_kind<QT_ACT_ELU, FIX64x2>(M, smem, tmem_base, phase, out); break;
+    case QT_ACT_LEAKY_RELU: mlp_forward_tc_kind<QT_ACT_LEAKY_RELU, FIX64x2>(M, smem, tmem_base, phase, out); break;
+    default: mlp_forward_tc_kind<QT_ACT_RELU, FIX64x2>(M, smem, tmem_base, phase, out); break;
     }
 }
 
@@ -608,14 +637,17 @@ __device__ __forceinline__ void stage_weights(const MlpDesc &M, const float *Wg,
 // network 2.40e9 against 2.19e9 env-steps/s); when the weights are too large to stage and stream from
 // L1/L2 instead, the deeper load prefetch that 255 registers allow wins (128-128: 4.0e8 against 2.4e8).
 // TILED: the warp-cooperative evaluation (64 accumulators per lane, two blocks per SM).
-// EVAL: 0 one episode per thread, 1 warp-cooperative tiles (both on the FP32 pipe, bit-identical), 2 the hidden layers
-// on the tensor cores (qt_policy_tc.cuh; the block's 128 episodes are one MMA operand, two blocks per SM).
+// EVAL: 0 one episode per thread, 1 warp-cooperative tiles (both on the FP32 pipe, bit-identical), 2 / 3 the hidden
+// layers on the tensor cores (qt_policy_tc.cuh; sets of 128 episodes are MMA operands, one 512-thread block per SM):
+// 2 = the reference's default shape, two hidden layers of 64 units, with layer count and widths as compile-time
+// constants; 3 = one to three hidden layers of any width up to 64 (run-time loops: 7 % slower on the 64-64 shape, and
+// keeping both forms in ONE kernel cost the fixed form its register allocation, hence two instantiations).
 template <int MOTION, int MINB, int EVAL>
-__global__ void __launch_bounds__(EVAL == 2 ? tc::kThreads : kPolicyThreads, MINB)
+__global__ void __launch_bounds__(EVAL >= 2 ? tc::kThreads : kPolicyThreads, MINB)
     rollout_policy_kernel(const __grid_constant__ qt_params P, const __grid_constant__ DynConsts C,
                           const __grid_constant__ MlpDesc M, const __grid_constant__ PolicyArgs A) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr bool TILED = EVAL == 1, TC = EVAL == 2;
+    constexpr bool TILED = EVAL == 1, TC = EVAL >= 2;
     constexpr int T = TC ? tc::kThreads : kPolicyThreads;
     const int64_t E = A.E;
     const int64_t e_raw = (int64_t)blockIdx.x * T + threadIdx.x;
@@ -623,9 +655,9 @@ __global__ void __launch_bounds__(EVAL == 2 ? tc::kThreads : kPolicyThreads, MIN
     uint32_t tmem_base = 0u, mma_phase = 0u;
     if constexpr (TC) {
         stage_weights_tc(M, A.W, smem_f);
-        uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_f + tc::kTmemSlot);
+        uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_f + M.tc.tmem_slot);
         if (threadIdx.x < 32) tc::tmem_alloc(tmem_slot);
-        if (threadIdx.x % tc::kRows == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(smem_f + tc::kBar) + threadIdx.x / tc::kRows, 1);
+        if (threadIdx.x % tc::kRows == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(smem_f + M.tc.bar) + threadIdx.x / tc::kRows, 1);
         tc::fence_async_smem();      // the staged weights are read by the tensor core
         tc::fence_before_sync();
         __syncthreads();
@@ -697,7 +729,7 @@ __global__ void __launch_bounds__(EVAL == 2 ? tc::kThreads : kPolicyThreads, MIN
         }
         float out[4];
         if constexpr (TC)
-            mlp_forward_tc(M, smem_f, tmem_base, mma_phase, out);
+            mlp_forward_tc<EVAL == 2>(M, smem_f, tmem_base, mma_phase, out);
         else if constexpr (TILED)
             mlp_forward_tiled(M, smem_f, tile0, tile1, feat, out);
         else if (A.w_in_smem)   // two inlined copies: one reads the weights with LDS, the other with LDG
@@ -886,7 +918,7 @@ static size_t smem_plan_tiled(const MlpDesc &M) {
 template <int MOTION, int MINB, int EVAL>
 static cudaError_t launch_policy_as(const qt_params &P, const DynConsts &C, const MlpDesc &M, const PolicyArgs &A,
                                     size_t smem, cudaStream_t st) {
-    constexpr int threads = EVAL == 2 ? tc::kThreads : kPolicyThreads;
+    constexpr int threads = EVAL >= 2 ? tc::kThreads : kPolicyThreads;
     const int64_t blocks = (A.E + threads - 1) / threads;
     cudaError_t e = cudaFuncSetAttribute(rollout_policy_kernel<MOTION, MINB, EVAL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -901,7 +933,11 @@ static cudaError_t launch_policy(const qt_params &P, const MlpDesc &M, PolicyArg
     C.init(P);
     too_wide = false;
     if (M.tc_ok && (P.debug_flags & QT_FLAG_POLICY_TENSOR_CORES) && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD))
-        return launch_policy_as<MOTION, 1, 2>(P, C, M, A, (size_t)tc::kFloats * sizeof(float), st);
+    {
+        const bool fix = M.tc.hidden == 2 && M.tc.n[0] == 64 && M.tc.n[1] == 64;
+        if (fix) return launch_policy_as<MOTION, 1, 2>(P, C, M, A, (size_t)M.tc.floats * sizeof(float), st);
+        return launch_policy_as<MOTION, 1, 3>(P, C, M, A, (size_t)M.tc.floats * sizeof(float), st);
+    }
     if (M.tiled && !(P.debug_flags & QT_DEBUG_POLICY_PER_THREAD) && smem_plan_tiled(M) <= 227 * 1024) {
         // three resident blocks (168 registers, the env state spills to L1 across the network evaluation)
         // when the shared memory allows, else two or one

@@ -20,9 +20,10 @@
 // Accuracy: dropping lo * lo and the truncation of lo to 11 bits leave a relative error of about 2^-21 per product —
 // the size of fp32 summation-order noise in a 64-term dot product — so this evaluation is NOT bit-identical to the
 // FP32-pipe evaluations (qt_policy.cu), which remain the default and the parity path; the tests bound the difference.
-// Shapes: two hidden layers of at most 64 units (the reference's default 64-64), zero padded to 64.
-// Shared memory per block: kSets x 32 KB (A heads, K = 64) + weights 44 KB (18->64 and 64->64, hi + lo) + 2 KB =
-// 174 KB with four sets: one block of 512 threads per SM.  TMEM: 128 columns per set (64 accumulators + 64 tails).
+// Shapes: one to three hidden layers of at most 64 units each (the reference's default 64-64, its "fast" 32-32), every
+// width zero padded to a multiple of 16 (a padded unit has zero weights and bias, so it outputs activation(0) = 0).
+// Shared memory per block: kSets x 32 KB (A heads, K = 64) + the split weights (64-64: 44 KB) + 2 KB = 174 KB with
+// four sets: one block of 512 threads per SM.  TMEM: 128 columns per set (64 accumulators + 64 tails).
 #pragma once
 #include <stdint.h>
 
@@ -35,28 +36,37 @@ namespace tc {
 constexpr int kSets = QT_TC_SETS;          // independent 128-episode sets per block
 constexpr int kRows = 128;                 // episodes per set = M of the MMA
 constexpr int kThreads = kSets * kRows;
-constexpr int kN = 64;                     // hidden width (padded)
+constexpr int kN = 64;                     // largest hidden width (a layer's width is padded to a multiple of 16)
+constexpr int kMaxHidden = 3;              // hidden layers on the tensor cores
 constexpr int kK0 = 24;                    // 18 features padded to a multiple of the MMA's K = 8
-constexpr int kK1 = 64;
+constexpr int kK1 = 64;                    // largest K of a later layer = largest width
 constexpr int kColsPerSet = 128;           // TMEM columns of a set: accumulator [0, 64) | A tails [64, 128)
 constexpr int kTmemCols = kSets * kColsPerSet <= 128 ? 128 : (kSets * kColsPerSet <= 256 ? 256 : 512);
 static_assert(kSets >= 1 && kSets <= 4, "512 TMEM columns hold four sets");
-// float offsets into the block's shared memory
+// Shared memory of a block (float offsets).  The A heads come first; what follows depends on the network's shape
+// and is laid out on the host (TcLayout, part of the kernel's MlpDesc argument).
 constexpr int kAHi = 0;                                  // [set][16 chunks][128 rows][4]
-constexpr int kB0Hi = kAHi + kSets * kRows * kK1;        // [6 chunks][64 units][4]
-constexpr int kB0Lo = kB0Hi + kN * kK0;
-constexpr int kB1Hi = kB0Lo + kN * kK0;                  // [16 chunks][64 units][4]
-constexpr int kB1Lo = kB1Hi + kN * kK1;
-constexpr int kW3 = kB1Lo + kN * kK1;                    // [64][4] output layer
-constexpr int kBias = kW3 + kN * 4;                      // b1[64] b2[64] b3[4]
-constexpr int kBar = kBias + 2 * kN + 4;                 // kSets mbarriers (8 bytes each, 8-byte aligned)
-constexpr int kTmemSlot = kBar + 2 * kSets;              // TMEM base address written by tcgen05.alloc
-constexpr int kFloats = kTmemSlot + 2;
-static_assert(kBar % 2 == 0, "mbarrier alignment");
+constexpr int kWeights = kAHi + kSets * kRows * kK1;     // B operands of the hidden layers, hi then lo per layer
+
+struct TcLayout {
+    int hidden;                  // hidden layers evaluated on the tensor cores (1..kMaxHidden)
+    int n[kMaxHidden];           // layer widths, padded to multiples of 16
+    int k[kMaxHidden];           // layer depths: 24 for the first, the previous width for the others
+    int b_hi[kMaxHidden];        // float offsets of the split weights [K / 4 chunks][N units][4]
+    int b_lo[kMaxHidden];
+    int w3;                      // output layer [64][4] fp32
+    int bias;                    // hidden biases [kMaxHidden][64], then the 4 output biases
+    int bar;                     // kSets mbarriers (8 bytes each, 8-byte aligned)
+    int tmem_slot;               // TMEM base address written by tcgen05.alloc
+    int floats;                  // total
+};
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
 // both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_for(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -68,26 +78,26 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            (1ull << 46);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
 // the same with the A operand in tensor memory (row i = lane i, one 32-bit column per K element)
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -226,19 +236,20 @@ __device__ __forceinline__ void store_chunk(float *a_hi, int row, int c, float x
     *reinterpret_cast<float4 *>(a_hi + (c * kRows + row) * 4) = hi;
 }
 
-// one layer's MMAs of one set: D[128][64] = A[128][K] B[64][K]', three TF32 products per k-step of 8; one thread
-__device__ __forceinline__ void issue_layer(const float *smem, int set, int b_hi, int b_lo, int ksteps, uint32_t set_tmem,
-                                            uint64_t *bar) {
+// one layer's MMAs of one set: D[128][N] = A[128][K] B[N][K]', three TF32 products per k-step of 8; one thread
+__device__ __forceinline__ void issue_layer(const float *smem, int set, int b_hi, int b_lo, int n, int ksteps,
+                                            uint32_t set_tmem, uint64_t *bar) {
     const uint32_t a_hi = smem_u32(smem + kAHi + set * kRows * kK1);
     const uint32_t bh = smem_u32(smem + b_hi), bl = smem_u32(smem + b_lo);
-    constexpr uint32_t kALbo = kRows * 16, kBLbo = kN * 16, kSbo = 128;
+    constexpr uint32_t kALbo = kRows * 16, kSbo = 128;
+    const uint32_t b_lbo = (uint32_t)n * 16, idesc = idesc_for(n);
     const uint32_t d_tmem = set_tmem, a_lo = set_tmem + 64;
     for (int ks = 0; ks < ksteps; ks++) {
         const uint64_t dah = smem_desc(a_hi + ks * 2 * kALbo, kALbo, kSbo);
-        const uint64_t dbh = smem_desc(bh + ks * 2 * kBLbo, kBLbo, kSbo), dbl = smem_desc(bl + ks * 2 * kBLbo, kBLbo, kSbo);
-        mma_tf32_ts(d_tmem, a_lo + ks * 8, dbh, ks > 0 ? 1u : 0u);
-        mma_tf32(d_tmem, dah, dbl, 1u);
-        mma_tf32(d_tmem, dah, dbh, 1u);
+        const uint64_t dbh = smem_desc(bh + ks * 2 * b_lbo, b_lbo, kSbo), dbl = smem_desc(bl + ks * 2 * b_lbo, b_lbo, kSbo);
+        mma_tf32_ts(d_tmem, a_lo + ks * 8, dbh, idesc, ks > 0 ? 1u : 0u);
+        mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+        mma_tf32(d_tmem, dah, dbh, idesc, 1u);
     }
     mma_commit(bar);
 }

@@ -97,7 +97,7 @@ class DeepTrackingPolicy(BaseController):
         self._packed_version = None
         self._dev = None
         # extension of the reference's config: evaluate the hidden layers on the tensor cores inside qt_rollout_policy
-        # (tcgen05, 3xTF32; networks with two hidden layers of at most 64 units; see include/qtrack.h
+        # (tcgen05, 3xTF32; networks with one to three hidden layers of at most 64 units; see include/qtrack.h
         # QT_FLAG_POLICY_TENSOR_CORES).  Off by default: the FP32-pipe evaluation is the parity path.
         self.tensor_cores = bool(config.get("tensor_cores", False))
         checkpoint_path = config.get("checkpoint_path")

@@ -450,7 +450,9 @@ def test_randomised_configurations_match_oracle(golden, gb, orc):
 
 
 @pytest.mark.parametrize("hidden,act,motion", [([64, 64], "relu", "linear"), ([48, 64], "tanh", "circular"),
-                                               ([64, 20], "elu", "stationary"), ([64, 64], "leaky_relu", "figure8")])
+                                               ([64, 20], "elu", "stationary"), ([64, 64], "leaky_relu", "figure8"),
+                                               ([32, 32], "relu", "sinusoidal"), ([64], "tanh", "linear"),
+                                               ([20, 40, 60], "elu", "circular"), ([16], "relu", "stationary")])
 def test_tensor_core_policy_evaluation_is_close_to_the_fp32_pipe(golden, gb, orc, hidden, act, motion):
     """QT_FLAG_POLICY_TENSOR_CORES: the two hidden layers as tcgen05 TF32 MMAs with the 3xTF32 split (x = hi + lo,
     fp32 accumulation in TMEM) against the FP32-pipe evaluation.  Not bit-identical by construction: each product
@@ -463,7 +465,7 @@ def test_tensor_core_policy_evaluation_is_close_to_the_fp32_pipe(golden, gb, orc
 
     from lqr_quadcopter_test_b200 import DeepTrackingPolicy
 
-    torch.manual_seed(len(hidden) * 77 + hidden[1])
+    torch.manual_seed(len(hidden) * 77 + hidden[-1])
     pol = DeepTrackingPolicy(config={"hidden_sizes": hidden, "activation": act})
     E = 1000
     env = EnvConfig()

@@ -1,7 +1,7 @@
 """Policy kernel, FP32-pipe (tiled FFMA2) evaluation against the tensor-core evaluation (tcgen05, 3xTF32) of the same
 64-64 fixture network: env-steps/s of both and the difference of their results.
 
-    python tools/time_policy_tc.py [episodes]
+    python tools/time_policy_tc.py [episodes] [hidden sizes, e.g. 32,32: a random-init relu network instead of the fixture]
 """
 import pathlib
 import sys
@@ -17,7 +17,13 @@ from lqr_quadcopter_test_b200 import EnvConfig, SuccessCriteria, _lib, rollout_d
 
 ctx = _lib.get_context()
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 2 * 128 * 4
-pol = gb.make_policy(np.load(ROOT / "tests" / "golden" / "policy.npz"), "relu_64_64")
+if len(sys.argv) > 2:
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy
+
+    torch.manual_seed(0)
+    pol = DeepTrackingPolicy(config={"hidden_sizes": [int(x) for x in sys.argv[2].split(",")], "activation": "relu"})
+else:
+    pol = gb.make_policy(np.load(ROOT / "tests" / "golden" / "policy.npz"), "relu_64_64")
 seeds = torch.arange(E, dtype=torch.int64, device=ctx.device) + 42
 for motion in ("stationary", "linear"):
     env = EnvConfig()
