@@ -126,3 +126,59 @@ def test_paired_square_root_is_ieee_sqrt(gpu_ctx):
     with np.errstate(invalid="ignore"):
         np.testing.assert_array_equal(ra.cpu().numpy(), np.sqrt(a))
         np.testing.assert_array_equal(rb.cpu().numpy(), np.sqrt(b))
+
+
+@pytest.mark.parametrize("n,batch,want_P", [(6, 1, True), (6, 33, False), (9, 31, True), (9, 65, False), (6, 1000, True)])
+def test_decoupled_dare_path_stays_in_bounds(gpu_ctx, n, batch, want_P):
+    """The decoupled DARE path (dare_blocks_kernel) writes its per-warp output tile with coalesced stores over whole
+    groups of 32 systems: the last, partial group must stop at the batch's end; P is optional."""
+    c = gpu_ctx
+    g = Guarded(c.device)
+    rng = np.random.default_rng(n + batch)
+    A = np.eye(n)
+    B = np.zeros((n, 4))
+    for k in range(3):
+        A[k, 3 + k] = 0.01
+        if n == 9:
+            A[6 + k, k] = 0.01
+    B[5, 0], B[4, 1], B[3, 2] = 0.01, -0.0981, 0.0981
+    Q = np.zeros((batch, n, n))
+    Q[:, np.arange(n), np.arange(n)] = rng.uniform(1e-4, 1e-2, (batch, n))
+    R = np.zeros((batch, 4, 4))
+    R[:, np.arange(4), np.arange(4)] = rng.uniform(0.1, 5.0, (batch, 4))
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=c.device)
+    Pm = g.alloc((batch, n, n)) if want_P else None
+    K = g.alloc((batch, 4, n))
+    iters, info = g.alloc((batch,), torch.int32), g.alloc((batch,), torch.int32)
+    c.dare_batched(n, 4, batch, dev(A), 0, dev(B), 0, dev(Q), n * n, dev(R), 16, Pm, K, iters, info)
+    g.check()
+    assert not bool(info.any()) and bool((iters > 5).all())
+    assert bool((K[:, 3, :] == 0).all()) and bool(K[:, 0, 5].abs().min() > 0)
+
+
+@pytest.mark.parametrize("E,hidden", [(1, [64, 64]), (513, [32, 32]), (1000, [64]), (129, [20, 40, 60])])
+def test_tensor_core_policy_rollout_stays_in_bounds(gpu_ctx, golden, E, hidden):
+    """qt_rollout_policy with QT_FLAG_POLICY_TENSOR_CORES: blocks of 512 episodes in four sets; partial last block and
+    partial last set, all logs on."""
+    from lqr_quadcopter_test_b200 import DeepTrackingPolicy
+
+    c = gpu_ctx
+    g = Guarded(c.device)
+    torch.manual_seed(E)
+    pol = DeepTrackingPolicy(config={"hidden_sizes": hidden})
+    env = EnvConfig()
+    env.target.motion_type = "linear"
+    prm = P.make_params(env, gc.controller_ns())
+    prm.debug_flags = P.FLAG_POLICY_TENSOR_CORES
+    K = torch.as_tensor(golden["dare"]["lqr_default_K"], dtype=torch.float64, device=c.device)
+    seeds = torch.arange(E, dtype=torch.int64, device=c.device) + 11
+    state0, tparams = g.alloc((12, E)), g.alloc((12, E))
+    c.reset_batched(prm, seeds, state0, tparams)
+    T, ts, ds = 60, 7, 9
+    tslots, dslots = (T + ts - 1) // ts, (T + ds - 1) // ds
+    metrics, final = g.alloc((16, E)), g.alloc((12, E))
+    traj = g.alloc((tslots, P.TRAJ_FIELDS, E))
+    feats, acts = g.alloc((dslots, E, 18), torch.float32), g.alloc((dslots, E, 4), torch.float32)
+    c.rollout_policy(prm, E, T, state0, tparams, pol.packed_mlp(), K, 6, E, metrics, final, traj, ts, tslots, feats, acts, ds, dslots)
+    g.check()
+    assert bool((metrics[0] == T).all()) and bool(torch.isfinite(final).all())
