@@ -24,7 +24,7 @@
 //  3. lane = block: G0 = b b' / r, H0 = diag(q); doubling on the S x S block in registers (Gauss-Jordan with the
 //     dense kernel's pivot rule) until ||dH||_F <= 1e-14 ||H||_F for the block; P block, gain row; results go
 //     to a per-warp output tile in shared memory.
-//  4. the tile (P [32][n][n], K [32][m][n], zero outside the blocks — exact zeros, which is what lets the rollout
+//  4. the tile (K [32][m][n], and P [32][n][n] when P is asked for; zero outside the blocks — exact zeros, which is what lets the rollout
 //     kernel's structure test accept the gain) is written to HBM with fully coalesced stores.
 // Convergence is tested per block (each block meets the tolerance on its own norm, which implies the dense
 // kernel's whole-matrix test); `iters` reports the largest count over the blocks of a system.
