@@ -360,6 +360,29 @@ class _GainController(BaseController):
     def get_control_components(self) -> dict | None:
         return self.last_control_components
 
+    def _feedforward_diagnostics(self, obs_vec: np.ndarray, has_acceleration: bool):
+        """Host restatement of the feedforward shaping for the DIAGNOSTICS dictionary only — the action itself comes
+        from the kernel (qt_step.cuh ``ctrl_action`` / ``pid_action``) and nothing computed here feeds back into it.
+        Returns (velocity-error with the scaled target velocity, clamped target velocity, FF acceleration term):
+        the target velocity is clamped to ``ff_max_velocity`` and scaled by 1 + ff_velocity_gain, the target
+        acceleration is clamped to ``ff_max_acceleration`` and scaled by ff_acceleration_gain
+        (controllers/__init__.py:300-336, riccati_lqr.py:832-862)."""
+        tv = obs_vec[15:18].copy()
+        ff_acc = np.zeros(3)
+        clamped = tv.copy()
+        if self.feedforward_enabled:
+            mag = float(np.linalg.norm(tv))
+            if mag > self.ff_max_velocity and mag > 0.0:
+                clamped = tv * (self.ff_max_velocity / mag)
+            tv = (1.0 + self.ff_velocity_gain) * clamped
+            if has_acceleration:
+                acc = obs_vec[18:21].copy()
+                amag = float(np.linalg.norm(acc))
+                if amag > self.ff_max_acceleration and amag > 0.0:
+                    acc = acc / amag * self.ff_max_acceleration
+                ff_acc = self.ff_acceleration_gain * acc
+        return tv - obs_vec[3:6], clamped, ff_acc
+
     def get_saturation_count(self) -> int:
         return self._saturation_count
 
@@ -393,9 +416,19 @@ class LQRController(_GainController):
 
     def compute_action(self, observation: dict) -> dict:
         _validate_observation(observation)
-        action, _, saturated = self._launch_scalar(observation_to_vector(observation), None)
+        obs_vec = observation_to_vector(observation)
+        action, _, saturated = self._launch_scalar(obs_vec, None)
         self._saturation_count += int(saturated)
-        self.last_control_components = {"is_saturated": saturated}
+        # diagnostics only (controllers/__init__.py:655-660)
+        vel_error, clamped_tv, ff_acc = self._feedforward_diagnostics(
+            obs_vec, observation["target"].get("acceleration", None) is not None)
+        ff_on = bool(self.feedforward_enabled)
+        self.last_control_components = {
+            "feedback_u": self.K @ np.concatenate([obs_vec[12:15] - obs_vec[0:3], vel_error]),
+            "ff_velocity_term": self.ff_velocity_gain * clamped_tv if ff_on else np.zeros(3),
+            "ff_acceleration_term": ff_acc,
+            "is_saturated": saturated,
+        }
         return dict(zip(ACTION_KEYS, (float(a) for a in action)))
 
     def reset(self) -> None:
@@ -451,7 +484,21 @@ class PIDController(_GainController):
         obs_vec = observation_to_vector(observation)
         action, state, _ = self._launch_scalar(obs_vec, self.state_vector())
         self.load_state_vector(state, True)
-        self.last_control_components = {"integral_error": self.integral_error.copy()}
+        # diagnostics only (controllers/__init__.py:296-354): the terms of the correction the kernel applied
+        vel_error, clamped_tv, ff_acc = self._feedforward_diagnostics(
+            obs_vec, observation["target"].get("acceleration", None) is not None)
+        p_term = self.kp_pos * (obs_vec[12:15] - obs_vec[0:3])
+        i_term = self.ki_pos * self.integral_error
+        d_term = self.kd_pos * vel_error
+        ff_on = bool(self.feedforward_enabled)
+        self.last_control_components = {
+            "p_term": p_term, "i_term": i_term, "d_term": d_term,
+            # the share of the D term that the scaled target velocity contributes
+            "ff_velocity_term": self.kd_pos * self.ff_velocity_gain * clamped_tv if ff_on else np.zeros(3),
+            "ff_acceleration_term": ff_acc,
+            "total_correction": p_term + i_term + d_term + ff_acc,
+            "integral_error": self.integral_error.copy(),
+        }
         return dict(zip(ACTION_KEYS, (float(a) for a in action)))
 
     def reset(self) -> None:
@@ -612,9 +659,17 @@ class RiccatiLQRController(_GainController):
             self.integral_state = new_integral
         self._saturation_count += int(saturated)
         # diagnostics only (never feeds back into the action): riccati_lqr.py:946-960
-        state_error = np.concatenate([obs_vec[12:15] - obs_vec[0:3], obs_vec[15:18] - obs_vec[3:6]])
+        vel_error, clamped_tv, ff_acc = self._feedforward_diagnostics(obs_vec, "acceleration" in observation["target"])
+        state_error = np.concatenate([obs_vec[12:15] - obs_vec[0:3], vel_error])
+        if lqi:
+            feedback_u = self.K_pd @ state_error + self.K_i @ self.integral_state
+        else:
+            feedback_u = self.K @ state_error
         self.last_control_components = {
             "state_error": state_error,
+            "feedback_u": feedback_u,
+            "ff_velocity_term": self.ff_velocity_gain * clamped_tv if self.feedforward_enabled else np.zeros(3),
+            "ff_acceleration_term": ff_acc,
             "K_matrix": self.K.copy(),
             "is_saturated": saturated,
         }

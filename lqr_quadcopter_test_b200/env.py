@@ -20,6 +20,7 @@ import numpy as np
 from . import _lib
 from . import params as P
 from .config import EnvConfig
+from .target_motion import TargetMotion
 
 logger = logging.getLogger(__name__)
 
@@ -164,6 +165,9 @@ class QuadcopterEnv:
         if seed is None:  # default_rng(None): fresh OS entropy
             seed = int.from_bytes(os.urandom(7), "little")
         self._batch.seeds.fill_(int(seed))
+        # quadcopter_env.py:89: the env's target generator is a public attribute; here a host view of the pattern the
+        # kernel drew (reset() below hands it the device's parameters)
+        self.target = TargetMotion(self.config.target, seed=int(seed))
         self._time = 0.0
         self._step_count = 0
         self._initialized = False
@@ -204,6 +208,8 @@ class QuadcopterEnv:
         b = self._batch
         obs = b.reset(None if seed is None else torch.tensor([int(seed)], dtype=torch.int64))
         self._obs_vec = obs.cpu().numpy().reshape(22)
+        self.target = TargetMotion(self.config.target, seed=int(b.seeds[0].item()))
+        self.target._tparams = b.tparams[:, 0].cpu().numpy().copy()
         self._time = 0.0
         self._step_count = 0
         self._history = []

@@ -250,7 +250,7 @@ class Evaluator:
         return summary
 
     def save_report(self, summary: EvaluationSummary, experiment_name: str | None = None) -> dict[str, Path]:
-        """eval.py:233-268 (metrics.json + text report; plots are out of scope)."""
+        """eval.py:233-268 (metrics.json + text report)."""
         if experiment_name is None:
             stamp = datetime.now(timezone.utc).strftime("%Y%m%d_%H%M%S")
             experiment_name = f"eval_{self.controller.name}_{stamp}"
@@ -263,6 +263,89 @@ class Evaluator:
         with open(report_path, "w") as f:
             f.write(format_metrics_report(summary))
         saved["report"] = report_path
+        return saved
+
+
+    # -- plots (eval.py:270-469; drawn by the package's own renderer, plots.py — matplotlib is not required) -------
+    def _episode_arrays(self, episode_idx: int):
+        n = len(self.episode_data_list)
+        if episode_idx >= n:
+            raise ValueError(f"Episode {episode_idx} not found (have {n} episodes)")
+        data = self.episode_data_list[episode_idx]
+        times = np.array([d["time"] for d in data], dtype=np.float64)
+        return data, times
+
+    def plot_trajectory(self, episode_idx: int = 0, save_path: str | Path | None = None, show_radius: bool = True):
+        """eval.py:270-340: x / y / z of vehicle and target over time (three stacked charts sharing the time axis),
+        with the target-radius band.  Returns (figure, axes)."""
+        from . import plots
+
+        data, times = self._episode_arrays(episode_idx)
+        quad = np.array([d["quadcopter_position"] for d in data], dtype=np.float64).reshape(-1, 3)
+        target = np.array([d["target_position"] for d in data], dtype=np.float64).reshape(-1, 3)
+        radius = self.criteria.target_radius
+        fig, axes = plots.subplots(3, 1, figsize=(12, 10), sharex=True)
+        for i, (ax, name, color) in enumerate(zip(axes, "XYZ", ("tab:blue", "tab:orange", "tab:green"))):
+            ax.plot(times, quad[:, i], label="Quadcopter", color=color, linewidth=1)
+            ax.plot(times, target[:, i], label="Target", color="red", linestyle="--", linewidth=1)
+            if show_radius:
+                ax.fill_between(times, target[:, i] - radius, target[:, i] + radius, alpha=0.2, color="green",
+                                label="Target Radius" if i == 0 else "")
+            ax.set_ylabel(f"{name} Position (m)")
+            ax.legend(loc="upper right")
+            ax.grid(True, alpha=0.3)
+        axes[-1].set_xlabel("Time (s)")
+        fig.suptitle(f"Position Tracking - Episode {episode_idx + 1}\nController: {self.controller.name}", fontsize=12)
+        if save_path:
+            fig.savefig(save_path, dpi=150)
+            logger.info("Saved trajectory plot: %s", save_path)
+        return fig, axes
+
+    def plot_tracking_error(self, episode_idx: int = 0, save_path: str | Path | None = None):
+        """eval.py:342-404: tracking error over time, the on-target samples marked, the target radius as a dashed
+        line.  Returns (figure, axes)."""
+        from . import plots
+
+        data, times = self._episode_arrays(episode_idx)
+        errors = np.array([d["tracking_error"] for d in data], dtype=np.float64)
+        on_target = np.array([d["on_target"] for d in data], dtype=bool)
+        radius = self.criteria.target_radius
+        fig, ax = plots.subplots(figsize=(12, 5))
+        ax.plot(times, errors, "b-", linewidth=1, label="Tracking Error")
+        ax.scatter(times[on_target], errors[on_target], c="green", s=2, alpha=0.5, label="On-Target")
+        ax.axhline(y=radius, color="r", linestyle="--", label=f"Target Radius ({radius}m)")
+        ax.set_xlabel("Time (s)")
+        ax.set_ylabel("Tracking Error (m)")
+        ax.set_title(f"Tracking Error - Episode {episode_idx + 1} | Controller: {self.controller.name}")
+        ax.legend()
+        ax.grid(True, alpha=0.3)
+        ax.set_ylim(bottom=0)
+        if save_path:
+            fig.savefig(save_path, dpi=150)
+            logger.info("Saved tracking error plot: %s", save_path)
+        return fig, ax
+
+    def generate_all_plots(self, summary: EvaluationSummary | None = None,
+                           experiment_name: str | None = None) -> list[Path]:
+        """eval.py:406-469: position-tracking and tracking-error plots of the best episode and, when it is another
+        one, of the worst episode, under ``<output_dir>/plots``.  Needs the per-step records
+        (``evaluate(record_trajectories=True)``, the default up to 32 episodes); returns the paths written."""
+        plots_dir = self.output_dir / "plots"
+        saved: list[Path] = []
+        n = len(self.episode_data_list)
+        if n == 0:
+            return saved
+        best = min(summary.best_episode_idx, n - 1) if summary is not None else 0
+        worst = min(summary.worst_episode_idx, n - 1) if summary is not None else 0
+        for tag, idx in (("best", best), ("worst", worst)):
+            if tag == "worst" and worst == best:
+                break
+            path = plots_dir / f"position_tracking_{tag}.png"
+            self.plot_trajectory(episode_idx=idx, save_path=path)
+            saved.append(path)
+            path = plots_dir / f"tracking_error_{tag}.png"
+            self.plot_tracking_error(episode_idx=idx, save_path=path)
+            saved.append(path)
         return saved
 
 

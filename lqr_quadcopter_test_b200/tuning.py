@@ -13,6 +13,7 @@ from __future__ import annotations
 import json
 import logging
 import os
+import pickle
 from dataclasses import dataclass, field, fields
 from datetime import datetime, timezone
 from itertools import product
@@ -294,6 +295,7 @@ class ControllerTuner:
         # strategy "cma_es": the reference needs the optional third-party `cma` package (tuning.py:636-643);
         # here the ask/tell loop is cmaes.py, so the strategy is always available
         self.cma_es = None
+        self._cma_checkpoint_path: Path | None = None
         self._cma_param_spec: list[tuple[str, int, tuple]] = []
 
     # -- candidate generation: host, identical RNG consumption to tuning.py:662-735 -----------------
@@ -603,6 +605,8 @@ class ControllerTuner:
             timestamp=datetime.now(timezone.utc).isoformat(), config=cfg.to_dict())
         if is_primary():          # one writer: N ranks would race on the same second-resolution file names
             self._save_results(result)
+            if cfg.strategy == "cma_es":
+                self._save_cma_checkpoint()
         barrier()
         return result
 
@@ -702,8 +706,25 @@ class ControllerTuner:
         x0 = self._get_cma_x0()
         ranges = [hi - lo for lo, hi in zip(lower, upper) if hi > lo]
         sigma0 = 1e-5 if not ranges else cfg.cma_sigma0 * float(np.exp(np.mean(np.log(ranges))))
-        self.cma_es = CMAEvolutionStrategy(x0, sigma0, lower, upper, seed=cfg.seed, popsize=cfg.cma_popsize,
-                                           tolfun=1e-11, tolx=1e-12, maxfevals=cfg.max_iterations)
+        # resume: the optimiser's state (mean, step size, covariance, generator) from the checkpoint that sits next to
+        # the results file being resumed (tuning.py:1357-1375)
+        self.cma_es = None
+        if cfg.resume_from:
+            checkpoint = Path(cfg.resume_from).parent / "cma_checkpoint.pkl"
+            if checkpoint.exists():
+                try:
+                    with open(checkpoint, "rb") as f:
+                        state = pickle.load(f)
+                    if isinstance(state, CMAEvolutionStrategy) and state.n == len(x0):
+                        self.cma_es = state
+                        self.cma_es.maxfevals = max(self.cma_es.maxfevals, self.cma_es.counteval + cfg.max_iterations)
+                        logger.info("Resumed CMA-ES state from %s", checkpoint)
+                except Exception as e:  # a damaged checkpoint only costs the optimiser's memory, not the run
+                    logger.warning("Failed to load CMA-ES checkpoint: %s", e)
+        if self.cma_es is None:
+            self.cma_es = CMAEvolutionStrategy(x0, sigma0, lower, upper, seed=cfg.seed, popsize=cfg.cma_popsize,
+                                               tolfun=1e-11, tolx=1e-12, maxfevals=cfg.max_iterations)
+        self._cma_checkpoint_path = self.output_dir / "cma_checkpoint.pkl"
         num_evals = len(self.results)
         while not self.cma_es.stop() and num_evals < cfg.max_iterations and not self.interrupted:
             solutions = self.cma_es.ask()[: cfg.max_iterations - num_evals]
@@ -717,6 +738,18 @@ class ControllerTuner:
             num_evals += len(solutions)
             if len(solutions) >= self.cma_es.mu:
                 self.cma_es.tell(solutions, [self.cma_es.penalised(x, -s) for x, s in zip(solutions, scores)])
+
+    def _save_cma_checkpoint(self) -> None:
+        """tuning.py:1430-1442: the optimiser object, pickled, for ``resume_from``."""
+        if self.cma_es is None or self._cma_checkpoint_path is None:
+            return
+        try:
+            self.output_dir.mkdir(parents=True, exist_ok=True)
+            with open(self._cma_checkpoint_path, "wb") as f:
+                pickle.dump(self.cma_es, f)
+            logger.info("Saved CMA-ES checkpoint to %s", self._cma_checkpoint_path)
+        except Exception as e:
+            logger.warning("Failed to save CMA-ES checkpoint: %s", e)
 
     def _save_results(self, result: TuningResult) -> None:
         """tuning.py:1103-1150: timestamped results + a stable "latest" copy."""

@@ -319,6 +319,30 @@ def test_cma_es_specification_and_convergence(tmp_path):
     assert es.best_f < 1e-9 and np.all(es.best_x >= lo) and np.all(es.best_x <= hi)
 
 
+def test_cma_es_checkpoint_round_trip(tmp_path):
+    """tuning.py:1357-1375 / 1430-1442: the optimiser object is pickled to <output_dir>/cma_checkpoint.pkl and a
+    restored copy continues with the same candidates (state and generator included)."""
+    import pickle
+
+    from lqr_quadcopter_test_b200.cmaes import CMAEvolutionStrategy
+
+    lo, hi = np.zeros(3), np.array([1.0, 2.0, 4.0])
+    es = CMAEvolutionStrategy([0.5, 1.0, 2.0], 0.3, lo, hi, seed=7, maxfevals=200)
+    f = lambda x: float(np.sum((x - 0.25 * hi) ** 2))
+    for _ in range(3):
+        X = es.ask()
+        es.tell(X, [es.penalised(x, f(es.repair(x))) for x in X])
+    t = ControllerTuner(TuningConfig(controller_type="pid", strategy="cma_es", output_dir=str(tmp_path / "out")))
+    t._save_cma_checkpoint()                                   # nothing to save yet: no file, no error
+    assert not (tmp_path / "out" / "cma_checkpoint.pkl").exists()
+    t.cma_es, t._cma_checkpoint_path = es, tmp_path / "out" / "cma_checkpoint.pkl"
+    t._save_cma_checkpoint()
+    with open(tmp_path / "out" / "cma_checkpoint.pkl", "rb") as fh:
+        back = pickle.load(fh)
+    assert back.generation == es.generation == 3 and back.counteval == es.counteval
+    np.testing.assert_array_equal(np.array(back.ask()), np.array(es.ask()))
+
+
 def test_bench_reference_arm_prints_exactly_one_json_line():
     """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line on stdout with the
     contract's keys; under torchrun only rank 0 prints."""
