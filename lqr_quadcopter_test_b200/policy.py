@@ -36,13 +36,20 @@ def _torch():
     return torch
 
 
-def make_policy_network(input_dim: int = 18, hidden_sizes=None, activation: str = "relu", output_bounds=None):
-    """deep_tracking_policy.py:24-147 as a torch module (parameters + training graph only)."""
+_POLICY_NETWORK_CLASS = None
+
+
+def _policy_network_class():
+    """deep_tracking_policy.py:24-147 as a torch module (parameters + training graph only).  The class is created on
+    first use so that importing this package does not import torch."""
+    global _POLICY_NETWORK_CLASS
+    if _POLICY_NETWORK_CLASS is not None:
+        return _POLICY_NETWORK_CLASS
     torch = _torch()
     nn = torch.nn
 
     class PolicyNetwork(nn.Module):
-        def __init__(self):
+        def __init__(self, input_dim: int = 18, hidden_sizes=None, activation: str = "relu", output_bounds=None):
             super().__init__()
             self.input_dim = input_dim
             self.hidden_sizes = list(hidden_sizes) if hidden_sizes is not None else [64, 64]
@@ -75,7 +82,19 @@ def make_policy_network(input_dim: int = 18, hidden_sizes=None, activation: str 
         def linear_layers(self):
             return [m for m in self.feature_extractor if isinstance(m, nn.Linear)] + [self.output_layer]
 
-    return PolicyNetwork()
+    _POLICY_NETWORK_CLASS = PolicyNetwork
+    return PolicyNetwork
+
+
+def make_policy_network(input_dim: int = 18, hidden_sizes=None, activation: str = "relu", output_bounds=None):
+    return _policy_network_class()(input_dim=input_dim, hidden_sizes=hidden_sizes, activation=activation,
+                                   output_bounds=output_bounds)
+
+
+def __getattr__(name: str):
+    if name == "PolicyNetwork":          # `from ...policy import PolicyNetwork` (controllers/__init__.py exports it)
+        return _policy_network_class()
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 class DeepTrackingPolicy(BaseController):

@@ -38,6 +38,7 @@ from . import params as P
 from .config import EnvConfig
 from .controller import LQRController, PIDController, RiccatiLQRController
 from .eval import VALID_CONTROLLER_TYPES, rollout_device
+from .losses import LossLogger, create_loss_from_config
 from .metrics import SuccessCriteria
 from .policy import DeepTrackingPolicy
 
@@ -104,41 +105,6 @@ class TrainingConfig:
         return {k: getattr(self, k) for k in self._FIELDS}
 
 
-class LossLogger:
-    """utils/losses.py LossLogger: per-epoch means of the logged components."""
-
-    def __init__(self):
-        self.current: dict[str, list[float]] = {}
-        self.history: list[dict[str, float]] = []
-
-    def log(self, losses: dict) -> None:
-        for k, v in losses.items():
-            self.current.setdefault(k, []).append(v)       # device tensors stay on the device until the epoch ends
-
-    def end_epoch(self) -> dict[str, float]:
-        out = {}
-        for k, vals in self.current.items():
-            if not vals:
-                continue
-            if any(hasattr(v, "detach") for v in vals):     # one read-back per component and epoch, not one per step
-                import torch
-
-                host = torch.stack([torch.as_tensor(v, dtype=torch.float64, device=vals[0].device) if not hasattr(v, "detach")
-                                    else v.detach().to(torch.float64) for v in vals]).cpu().numpy()
-                out[k] = float(np.mean(host))
-            else:
-                out[k] = float(np.mean(vals))
-        self.history.append(out)
-        self.current = {}
-        return out
-
-    def get_best_epoch(self, key: str = "total") -> tuple[int, float]:
-        vals = [(i, h[key]) for i, h in enumerate(self.history) if key in h and not math.isnan(h[key])]
-        if not vals:
-            return -1, float("inf")
-        return min(vals, key=lambda t: t[1])
-
-
 def _weighted_error(torch, err, weight: float, kind: str, delta: float = 1.0):
     """TrackingLoss._compute_weighted_error (utils/losses.py) for scalar weights (weight * I)."""
     weighted = err * weight
@@ -173,8 +139,17 @@ class Trainer:
         self.env_config.target.motion_type = config.target_motion_type
         self.env_config.success_criteria.target_radius = config.target_radius
         self.criteria = SuccessCriteria(target_radius=config.target_radius)
+        from .env import QuadcopterEnv
+
+        self.env = QuadcopterEnv(config=self.env_config)     # train.py:300: scalar view of the same configuration
         self.optimizer = self._create_optimizer() if self.is_deep_controller else None
         self.loss_logger = LossLogger()
+        # the reference's loss object (train.py:318-330), kept for callers that inspect it; the optimiser step below
+        # evaluates the same terms on the roll-out batches
+        self.loss_fn = create_loss_from_config({
+            "position_weight": config.position_weight, "velocity_weight": config.velocity_weight,
+            "control_weight": config.control_weight, "error_type": config.error_type,
+            "target_radius": config.target_radius, "device": str(self.device)})
         self.experiment_log: list[dict] = []
         self.checkpoint_dir = Path(config.checkpoint_dir)
         if self.is_deep_controller:

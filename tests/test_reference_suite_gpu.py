@@ -9,7 +9,8 @@ package tests/refshim/ — i.e. every `from quadcopter_tracking... import X` in 
 Files run, whole (every class in them; /root/reference/tests): test_env_dynamics.py (target motion, env, PID / LQR /
 Riccati-LQR / feedforward / LQI controllers, hover-thrust and axis-sign integration, ENU frame helpers),
 test_eval.py (metrics, summaries, Evaluator incl. its plots, load_controller, controller selection, action schema,
-LQI evaluation) and test_tuning.py (search space, tuner strategies incl. CMA-ES and its checkpoint, Riccati tuning).
+LQI evaluation), test_tuning.py (search space, tuner strategies incl. CMA-ES and its checkpoint, Riccati tuning) and
+test_training_loop.py (policy network, losses, Trainer and its modes; its TestDiagnostics class is a listed deviation).
 SURVEY.md §8(c) names the classes TestTargetMotion, TestQuadcopterEnv, TestRiccatiLQR* / TestRiccatiLQI,
 TestRiccatiControllerSelection, TestLQIController and TestRiccatiTuning; they are part of these files.
 The reference itself passes all but one of them (a reference bug — the test expects the message
@@ -34,7 +35,7 @@ pytestmark = pytest.mark.gpu
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 REF_TESTS = ROOT / "baseline" / "_ref" / "reference_tests"
 
-FILES = ["test_env_dynamics.py", "test_eval.py", "test_tuning.py"]
+FILES = ["test_env_dynamics.py", "test_eval.py", "test_tuning.py", "test_training_loop.py"]
 
 # test name -> why it does not pass against the drop-in (each is a deliberate, documented difference or a reference bug)
 KNOWN_DEVIATIONS = {
@@ -42,6 +43,14 @@ KNOWN_DEVIATIONS = {
                                           "matches 'q_int must have 3 elements' but riccati_lqr.py:583-587 (and the drop-in, "
                                           "which reproduces that message) say 'exactly 3 elements'",
 }
+# TestDiagnostics (test_training_loop.py:974-1290) exercises utils/diagnostics.py, the training-diagnostics recorder
+# SURVEY.md §2 marks out of scope; it is not built and its thirteen tests are listed, not hidden
+KNOWN_DEVIATIONS.update({name: "out of scope (SURVEY.md §2): the training diagnostics module utils/diagnostics.py is not built"
+                         for name in (
+    "test_diagnostics_config_defaults", "test_diagnostics_config_from_dict", "test_diagnostics_disabled_by_default",
+    "test_diagnostics_enabled_logging", "test_diagnostics_gradient_stats", "test_diagnostics_observation_stats",
+    "test_diagnostics_observation_stats_handles_nan", "test_diagnostics_action_stats", "test_diagnostics_save_files",
+    "test_training_with_diagnostics_enabled", "test_diagnostics_throttling", "test_diagnostics_max_entries_per_epoch")})
 
 
 def test_reference_test_classes_pass_against_the_drop_in(gpu_ctx, tmp_path):
@@ -99,7 +108,7 @@ def test_reference_test_classes_pass_against_the_drop_in(gpu_ctx, tmp_path):
         print(f"[conformance]   FAILED {cls.split('.')[-1]}::{name}: {KNOWN_DEVIATIONS.get(name, 'UNEXPECTED: ' + msg)}")
     for name in skipped:
         print(f"[conformance]   skipped {name}")
-    assert total >= 300, f"only {total} reference tests were collected\n{r.stdout[-2000:]}"
+    assert total >= 400, f"only {total} reference tests were collected\n{r.stdout[-2000:]}"
     assert not unexpected, f"reference tests failing against the drop-in: {unexpected}\n{r.stdout[-6000:]}"
     assert len(passed) >= total - len(KNOWN_DEVIATIONS)
 
