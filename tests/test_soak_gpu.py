@@ -55,8 +55,10 @@ def lqi_tolerance(ref_final_state):
     return np.maximum(gc.TOL_LQI, 1e-10 * np.abs(ref_final_state).max(axis=0))
 
 
-def compare_at_scale(got, ref, tol_per_episode, label, max_borderline_frac=1e-3):
-    """Asserts the north-star parity statement and returns the report line."""
+def compare_at_scale(got, ref, tol_per_episode, label, max_borderline_frac=1e-3, soft_counter_frac=0.0):
+    """Asserts the north-star parity statement and returns the report line.  ``soft_counter_frac`` > 0 (only the
+    ill-conditioned figure-8 feedforward case) lets the overshoot / saturation counts differ in that fraction of the
+    episodes; steps, termination codes and violation counts must always be identical."""
     M, G = got["metrics"], ref["metrics"]
     E = M.shape[1]
     per_ep = np.abs(got["final_state"] - ref["final_state"]).max(axis=0)
@@ -73,7 +75,9 @@ def compare_at_scale(got, ref, tol_per_episode, label, max_borderline_frac=1e-3)
     print(line, flush=True)
     assert above == 0, line
     assert flags == 0, line
-    assert other == 0, line
+    hard = sum(int((M[r] != G[r]).sum()) for r in (P.M_STEPS, P.M_TERMINATION, P.M_VIOLATIONS))
+    assert hard == 0, line
+    assert other <= int(soft_counter_frac * E), line
     assert borderline <= max(1, int(max_borderline_frac * E)), line
     assert diff_on.max() <= 2, line                       # a borderline episode moves single samples, not runs
     same = diff_on == 0
@@ -103,6 +107,49 @@ def test_full_episodes_against_the_oracle(gb, orc, label, cfg, motion):
     tol = lqi_tolerance(ref["final_state"]) if cfg else np.full(E, gc.TOL_LQR)
     compare_at_scale(got, ref, tol, label)
     assert (got["metrics"][P.M_STEPS] == 3000).all()
+
+
+@pytest.mark.parametrize("label,kind,cfg,motion,integrator", [
+    ("PID, linear target", "pid", {}, "linear", "rk4"),
+    ("PID with integral action (clamped), stationary target", "pid", {"ki_pos": [0.002, 0.002, 0.5], "integral_limit": 0.4},
+     "stationary", "rk4"),
+    ("PID with feedforward, circular target", "pid", gc.PID_LQR_CASES["pidff_circular"][3], "circular", "rk4"),
+    ("heuristic LQR, figure-8 target", "lqr", {}, "figure8", "rk4"),
+    ("heuristic LQR with feedforward, sinusoidal target", "lqr", gc.PID_LQR_CASES["hlqrff_sinusoidal"][3], "sinusoidal", "rk4"),
+    ("Riccati-LQR with feedforward, sinusoidal target", "riccati_lqr",
+     {"feedforward_enabled": True, "ff_velocity_gain": [0.1, 0.1, 0.05], "ff_acceleration_gain": [0.05, 0.05, 0.0]}, "sinusoidal", "rk4"),
+    ("Riccati-LQR with acceleration feedforward, figure-8 target (ill-conditioned by construction)", "riccati_lqr",
+     {"feedforward_enabled": True, "ff_velocity_gain": [0.1, 0.1, 0.05], "ff_acceleration_gain": [0.05, 0.05, 0.0]}, "figure8", "rk4"),
+    ("Riccati-LQR, Euler integrator, linear target", "riccati_lqr", {}, "linear", "euler"),
+])
+def test_other_controllers_and_the_full_kernel_variant_against_the_oracle(gb, orc, label, kind, cfg, motion, integrator):
+    """SURVEY.md §8(f).1 and the FULL variant of the rollout kernel at scale: PID (controllers/__init__.py:243-379, with
+    and without integral action and feedforward), the heuristic LQR (:575-700), feedforward through the Riccati law
+    (riccati_lqr.py:832-862), the figure-8 target (target_motion.py:170-215) and the Euler integrator
+    (quadcopter_env.py:295-330) — full 30 s episodes against the oracle with the bounds of the Riccati cases."""
+    from lqr_quadcopter_test_b200 import SuccessCriteria, load_controller
+
+    E = max(8192, E_SOAK // 2)
+    env = EnvConfig()
+    env.target.motion_type = motion
+    env.simulation.integrator = integrator
+    ctrl = load_controller(kind, config=dict(cfg))
+    prm = ctrl.kernel_params(env, SuccessCriteria())
+    s0, tp = orc.reset_reference(prm, np.arange(7, 7 + E))
+    K = np.ascontiguousarray(ctrl.effective_gain())
+    ref = orc.rollout(prm, s0, tp, K, max_steps=3002, n_threads=os.cpu_count() or 8)
+    got = gb.rollout(prm, s0, tp, K, max_steps=3002)
+    if motion == "figure8" and cfg.get("feedforward_enabled"):
+        # The reference's figure-8 ACCELERATION is a forward difference of a forward difference with h = 1e-6
+        # (target_motion.py:209-229): one ulp of sin / cos is amplified by 1 / h^2 = 1e12 to ~1e-4 m/s^2, so this one
+        # output depends on the libm at hand — numpy's, glibc's (the oracle) and the kernel's each round a few
+        # arguments differently.  Only acceleration feedforward reads it: with gain 0.05 the actions move by ~5e-6 and
+        # the 30 s closed loop by ~6e-5 m (the oracle itself is 1.3e-6 from the reference after 3000 steps of seed 7).
+        # Stated tolerance for this combination: 5e-4 m; flags, steps, terminations and violations stay identical.
+        compare_at_scale(got, ref, np.full(E, gc.TOL_FIGURE8_FF), label, max_borderline_frac=0.01, soft_counter_frac=0.01)
+    else:
+        compare_at_scale(got, ref, np.full(E, gc.TOL_LQR), label)
+    assert (got["metrics"][P.M_STEPS] == ref["metrics"][P.M_STEPS]).all()
 
 
 def test_sweep_candidates_against_the_oracle(gb, orc):
