@@ -370,3 +370,71 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     r1 = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, env=env, timeout=300)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_coordinate_frame_helpers():
+    """utils/coordinate_frame.py:44-405: ENU constants and the assertions built on them."""
+    from lqr_quadcopter_test_b200 import coordinate_frame as cf
+
+    assert (cf.AXIS_X, cf.AXIS_Y, cf.AXIS_Z) == (0, 1, 2) and cf.get_current_frame() is cf.ENU_FRAME
+    assert str(cf.ENU_FRAME) == "ENU: X=East, Y=North, Z=Up" and cf.NED_FRAME.gravity_sign == "+"
+    cf.assert_gravity_direction_enu([0.0, 0.0, -9.81])
+    cf.assert_thrust_direction_enu([0.0, 0.0, 0.0])
+    with pytest.raises(cf.ENUFrameError, match="should point in -Z"):
+        cf.assert_gravity_direction_enu([0.0, 0.0, 9.81])
+    with pytest.raises(cf.ENUFrameError, match="zero magnitude"):
+        cf.assert_gravity_direction_enu(np.zeros(3))
+    with pytest.raises(cf.ENUFrameError, match=r"should point in \+Z"):
+        cf.assert_thrust_direction_enu([0.0, 0.0, -1.0])
+    cf.assert_control_signs_enu([1.0, -1.0, 0.0], pitch_rate=0.2, roll_rate=0.3)          # +x -> +pitch, -y -> +roll
+    cf.assert_control_signs_enu([0.3, 0.3, 0.0], pitch_rate=-1.0, roll_rate=1.0)          # below the 0.5 m threshold
+    with pytest.raises(cf.ENUFrameError, match=r"\+Y error"):
+        cf.assert_control_signs_enu([0.0, 1.0, 0.0], 0.0, 0.5)
+    with pytest.raises(cf.ENUFrameError, match="-X error"):
+        cf.assert_control_signs_enu([-0.3, 0.0, 0.0], 0.0, 0.0, error_threshold=0.2)
+    with pytest.raises(cf.ENUFrameError, match="Z-axis.*below minimum"):
+        cf.assert_z_up([0.0, 0.0, -150.0])
+    with pytest.raises(cf.ENUFrameError, match="Target Z position.*very negative"):
+        cf.validate_observation_frame({"quadcopter": {"position": [0, 0, 1.0]}, "target": {"position": [0, 0, -50.0]}})
+    assert cf.validate_observation_frame({"quadcopter": {"position": [0, 0, 1.0]}, "target": {"position": [1, 1, 2.0]}})
+    assert cf.compute_expected_hover_thrust(2.0) == 19.62
+    np.testing.assert_array_equal(cf.compute_position_error_enu([0, 0, 1.0], [2, 3, 4.0]), [2.0, 3.0, 3.0])
+
+
+def test_training_losses_on_cpu_tensors():
+    """utils/losses.py:25-406: the three error kinds, matrix weights, imitation target, reward shaping, the combined
+    total and the per-epoch logger — against closed forms."""
+    import torch
+
+    from lqr_quadcopter_test_b200.losses import (CombinedLoss, LossLogger, RewardShapingLoss, TrackingLoss,
+                                                 create_loss_from_config)
+
+    pe = torch.tensor([[1.0, 2.0, 2.0], [0.0, 0.0, 0.0]])
+    ve, act = torch.zeros(2, 3), torch.tensor([[1.0, 0.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]])
+    out = TrackingLoss(position_weight=np.diag([2.0, 1.0, 1.0]), velocity_weight=0.1, control_weight=0.5)(pe, ve, act)
+    assert float(out["position"]) == pytest.approx((2 * 1 + 4 + 4) / 2) and float(out["control"]) == pytest.approx(0.5)
+    assert float(out["total"]) == pytest.approx(float(out["position"] + out["velocity"] + out["control"]))
+    assert float(TrackingLoss(error_type="l1")(pe, ve, act)["position"]) == pytest.approx(5.0 / 2)
+    hub = TrackingLoss(error_type="huber", huber_delta=1.0)(pe, ve, act)["position"]        # |e| = 3 and 0
+    assert float(hub) == pytest.approx((1.0 * (3.0 - 0.5) + 0.0) / 2)
+    imit = TrackingLoss(control_weight=1.0)(pe, ve, act, action_target=act)
+    assert float(imit["control"]) == 0.0
+    with pytest.raises(ValueError, match="Unknown error type"):
+        TrackingLoss(error_type="l3")(pe, ve, act)
+    r = RewardShapingLoss(target_radius=0.5, on_target_bonus=2.0, distance_penalty=1.0)(torch.tensor([0.25, 1.0]))
+    assert r["on_target"].tolist() == [True, False] and float(r["reward"]) == pytest.approx((2.0 - 0.25 - 1.0) / 2)
+    assert float(RewardShapingLoss(smoothing="exp")(torch.tensor(0.0))["penalty"]) == 0.0
+    c = create_loss_from_config({"position_weight": 2.0, "error_type": "huber", "target_radius": 0.3, "reward_weight": 0.5})
+    assert isinstance(c, CombinedLoss) and c.tracking_loss.error_type == "huber" and c.reward_loss.target_radius == 0.3
+    full = c(pe, ve, act, tracking_error=pe.norm(dim=-1))
+    assert float(full["total"]) == pytest.approx(float(full["tracking_total"]) - 0.5 * float(full["reward"]))
+    assert float(full["on_target_ratio"]) == 0.5
+    pe.requires_grad_(True)
+    CombinedLoss()(pe, ve, act, tracking_error=pe.norm(dim=-1))["total"].backward()
+    assert pe.grad is not None and torch.isfinite(pe.grad).all()
+    log = LossLogger()
+    for v in (1.0, torch.tensor(3.0)):
+        log.log({"total": v})
+    assert log.end_epoch() == {"total": 2.0} and log.get_history() == [{"total": 2.0}] and log.get_best_epoch() == (0, 2.0)
+    log.reset()
+    assert log.get_history() == [] and log.get_best_epoch() == (-1, float("inf"))
