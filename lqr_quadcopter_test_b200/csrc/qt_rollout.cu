@@ -37,6 +37,9 @@ constexpr int kRolloutThreads = 128;
 #ifndef QT_OPT_FINITE
 #define QT_OPT_FINITE 1   // structured loop: no per-step non-finite tests (proved impossible once per episode)
 #endif
+#ifndef QT_RESYNC_MASK
+#define QT_RESYNC_MASK 15  // the carried sin / cos (attitude, target pattern) are re-evaluated directly every 16th step
+#endif
 #ifndef QT_ROLLOUT_MIN_BLOCKS
 #define QT_ROLLOUT_MIN_BLOCKS 4  // resident blocks per SM the register allocator must allow (128 registers)
 #endif
@@ -382,17 +385,17 @@ __global__ void __launch_bounds__(kRolloutThreads, QT_ROLLOUT_MIN_BLOCKS)
             if (kRebaseInline && !euler) {
                 // Bnext belongs to the attitude the integrator produced; the constraints usually only re-round it
                 // ((a + pi) - pi, <= 2.3e-16).  A wrap, a clip or the periodic re-synchronisation evaluates directly.
-                if (attitude_changed || (step & 15) == 15)
+                if (attitude_changed || (step & QT_RESYNC_MASK) == QT_RESYNC_MASK)
                     trig_rebase<FAST>(eta_old, s, true, B);
                 else
                     B = Bnext;
             } else {
-                trig_rebase<FAST>(eta_old, s, (step & 15) == 15, B);
+                trig_rebase<FAST>(eta_old, s, (step & QT_RESYNC_MASK) == QT_RESYNC_MASK, B);
             }
             {
                 const double t_old = t;
                 t += C.dt;
-                tg.trig_advance(t_old, t, (step & 15) == 15);
+                tg.trig_advance(t_old, t, (step & QT_RESYNC_MASK) == QT_RESYNC_MASK);
             }
             tg.template state<FULL>(P, t, tp, tv, ta);
             {
