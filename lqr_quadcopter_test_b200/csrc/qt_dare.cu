@@ -314,6 +314,18 @@ struct DareCfg {
     static constexpr int WARPS = RN <= 20 ? 4 : 3;
     static constexpr int MIN_BLOCKS = RN <= 12 ? 3 : 2;
 };
+#if defined(QT_DARE_W16) && defined(QT_DARE_B16)   // A/B: block shape of the n = 13..16 kernel
+template <>
+struct DareCfg<16, QT_DARE_R16> {
+    static constexpr int RN = 16 * QT_DARE_R16, WARPS = QT_DARE_W16, MIN_BLOCKS = QT_DARE_B16;
+};
+#endif
+#if defined(QT_DARE_W12) && defined(QT_DARE_B12)   // A/B: block shape of the n = 10..12 kernel
+template <>
+struct DareCfg<12, QT_DARE_R12> {
+    static constexpr int RN = 12 * QT_DARE_R12, WARPS = QT_DARE_W12, MIN_BLOCKS = QT_DARE_B12;
+};
+#endif
 #if defined(QT_DARE_W6) && defined(QT_DARE_B6)   // A/B: block shape of the n = 6 kernel
 template <>
 struct DareCfg<6, QT_DARE_R6> {
