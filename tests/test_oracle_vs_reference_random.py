@@ -12,6 +12,7 @@ without either the test is skipped.  The one combination that cannot be pinned a
 tested for what it is: acceleration feedforward on the figure-8 target (finite-difference acceleration with
 h = 1e-6: one ulp of libm's sin / cos becomes ~1e-4 m/s^2; tests/test_soak_gpu.py states its tolerance).
 """
+import os
 import pathlib
 import sys
 
@@ -105,7 +106,7 @@ def apply_env(cfg_obj, env):
 
 def test_oracle_tracks_the_reference_on_random_configurations(ref):
     rng = np.random.default_rng(20260119)
-    n_cases, n_steps = 40, 300
+    n_cases, n_steps = int(os.environ.get("QT_RANDOM_CASES", 40)), 300      # soak: QT_RANDOM_CASES=400
     worst = {}
     for case in range(n_cases):
         env, kind, cfg = draw_case(rng)
@@ -147,6 +148,6 @@ def test_oracle_tracks_the_reference_on_random_configurations(ref):
         assert int(out["metrics"][P.M_ENV_ON_TARGET, 0]) == round(info["on_target_ratio"] * steps), label
         assert int(out["metrics"][P.M_VIOLATIONS, 0]) == info["action_violations"], label
         worst[kind] = max(worst.get(kind, 0.0), diff)
-    print("[parity] oracle vs live reference on 40 random configurations x 300 steps, worst |state difference| per law: "
+    print(f"[parity] oracle vs live reference on {n_cases} random configurations x {n_steps} steps, worst |state difference| per law: "
           + ", ".join(f"{k} {v:.1e}" for k, v in sorted(worst.items())))
     assert set(worst) == {"riccati_lqr", "lqi", "pid", "lqr"}      # the draw covered every control law
