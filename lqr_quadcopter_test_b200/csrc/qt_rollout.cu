@@ -21,7 +21,10 @@
 
 namespace qt {
 
-constexpr int kRolloutThreads = 128;
+#ifndef QT_ROLLOUT_THREADS
+#define QT_ROLLOUT_THREADS 128   // A/B hook (profiles/r02_rollout_ab.txt); the fused candidate scores need a divisor-rich block size
+#endif
+constexpr int kRolloutThreads = QT_ROLLOUT_THREADS;
 #ifndef QT_OPT_KREG
 #define QT_OPT_KREG 1
 #endif
